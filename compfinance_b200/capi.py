@@ -1,0 +1,198 @@
+"""ctypes binding of compfinance_b200/lib/libcf_b200.so (include/cf_b200.h).
+
+Plumbing only: Python here plays the role of a foreign-language caller of the C ABI (tests, bench).
+There is no CPU fallback: if the CUDA library is missing, import fails loudly; if no GPU is present,
+every compute call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcf_b200.so")
+
+CF_RNG_SOBOL, CF_RNG_MRG32K3A = 0, 1
+CF_MODEL_BS, CF_MODEL_DUPIRE, CF_MODEL_DISPLACED = 0, 1, 2
+CF_PRODUCT_EUROPEAN, CF_PRODUCT_UOC, CF_PRODUCT_EUROPEANS = 0, 1, 2
+CF_PRODUCT_BASKETS, CF_PRODUCT_AUTOCALL, CF_PRODUCT_MULTISTATS = 3, 4, 5
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+class cf_rng(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("seed1", C.c_uint32), ("seed2", C.c_uint32)]
+
+
+class cf_model(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("n_assets", C.c_int32), ("n_steps", C.c_int32), ("n_events", C.c_int32),
+        ("is_event", _u8p), ("spot", C.c_double),
+        ("bs_drifts", _dp), ("bs_stds", _dp),
+        ("numeraires", _dp), ("fwd_factors", _dp), ("discounts", _dp),
+        ("n_knots", C.c_int32), ("log_spots", _dp), ("interp_vols", _dp),
+        ("dlm_spots", _dp), ("dlm_chol", _dp), ("dlm_alphas", _dp), ("dlm_dynamics", _ip),
+        ("dlm_dyn_fwd", _dp), ("dlm_drifts", _dp), ("dlm_stds", _dp), ("dlm_fwd_factors", _dp),
+    ]
+
+
+class cf_product(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("n_events", C.c_int32), ("n_payoffs", C.c_int32), ("is_put", C.c_int32),
+        ("strike", C.c_double), ("barrier", C.c_double), ("smooth", C.c_double), ("coupon", C.c_double),
+        ("strike_offsets", _ip), ("strikes", _dp), ("weights", _dp), ("event_dt", _dp),
+    ]
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m compfinance_b200.build` "
+                          "(the engine has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.cf_last_error.restype = C.c_char_p
+    lib.cf_launch_count.restype = C.c_uint64
+    lib.cf_table_adjoint_size.restype = C.c_size_t
+    lib.cf_table_adjoint_size.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product)]
+    lib.cf_plan_out_size.restype = C.c_size_t
+    lib.cf_plan_out_size.argtypes = [C.c_void_p, C.c_int]
+    lib.cf_sobol_direction_number.restype = C.c_uint32
+    lib.cf_plan_create.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product), C.POINTER(cf_rng), C.POINTER(C.c_void_p)]
+    lib.cf_plan_destroy.argtypes = [C.c_void_p]
+    lib.cf_plan_destroy.restype = None
+    lib.cf_plan_launch_value.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.cf_plan_launch_aad.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.cf_plan_kernel_ms.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int)]
+    lib.cf_run_value.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product), C.POINTER(cf_rng), C.c_uint64,
+                                 C.c_uint64, _dp, _dp]
+    lib.cf_run_aad.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product), C.POINTER(cf_rng), C.c_uint64,
+                               C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.cf_sobol_states.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.cf_rng_draw.argtypes = [C.POINTER(cf_rng), C.c_int, C.c_uint64, C.c_uint64, C.c_int, _dp]
+    lib.cf_mrg_numerators.argtypes = [C.POINTER(cf_rng), C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.cf_inv_normal.argtypes = [_dp, _dp, C.c_uint64]
+    lib.cf_init.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    return lib
+
+
+EXPORTED = [
+    "cf_init", "cf_shutdown", "cf_last_error", "cf_launch_count", "cf_table_adjoint_size", "cf_run_value",
+    "cf_run_aad", "cf_plan_create", "cf_plan_destroy", "cf_plan_launch_value", "cf_plan_launch_aad",
+    "cf_plan_out_size", "cf_plan_kernel_ms", "cf_sobol_states", "cf_sobol_direction_number", "cf_sobol_max_dim",
+    "cf_rng_draw", "cf_mrg_numerators", "cf_inv_normal",
+]
+
+
+class CfError(RuntimeError):
+    pass
+
+
+class Engine:
+    """Convenience wrapper over the C ABI taking numpy arrays."""
+
+    def __init__(self, device=None):
+        self.lib = load()
+        self._keep = []
+        if device is not None:
+            dev = (C.c_int * 1)(int(device))
+            self._chk(self.lib.cf_init(1, dev))
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise CfError(self.lib.cf_last_error().decode())
+
+    @staticmethod
+    def _d(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return a, a.ctypes.data_as(_dp)
+
+    def rng(self, kind, seed1=12345, seed2=12346):
+        return cf_rng(CF_RNG_SOBOL if kind == "sobol" else CF_RNG_MRG32K3A, seed1, seed2)
+
+    def dupire_model(self, spot, log_spots, interp_vols, is_event, n_events):
+        keep = []
+        ls, pls = self._d(log_spots); keep.append(ls)
+        iv, piv = self._d(interp_vols); keep.append(iv)
+        ev = np.ascontiguousarray(is_event, dtype=np.uint8); keep.append(ev)
+        m = cf_model()
+        m.kind, m.n_assets, m.n_steps, m.n_events = CF_MODEL_DUPIRE, 1, iv.shape[0], n_events
+        m.is_event = ev.ctypes.data_as(_u8p)
+        m.spot, m.n_knots, m.log_spots, m.interp_vols = spot, ls.size, pls, piv
+        m._keep = keep
+        return m
+
+    def bs_model(self, spot, drifts, stds, is_event, numeraires, fwd_factors, discounts):
+        keep = []
+        dr, pdr = self._d(drifts); keep.append(dr)
+        st, pst = self._d(stds); keep.append(st)
+        nu, pnu = self._d(numeraires); keep.append(nu)
+        ff, pff = self._d(fwd_factors); keep.append(ff)
+        di, pdi = self._d(discounts); keep.append(di)
+        ev = np.ascontiguousarray(is_event, dtype=np.uint8); keep.append(ev)
+        m = cf_model()
+        m.kind, m.n_assets, m.n_steps, m.n_events = CF_MODEL_BS, 1, dr.size, nu.size
+        m.is_event = ev.ctypes.data_as(_u8p)
+        m.spot, m.bs_drifts, m.bs_stds = spot, pdr, pst
+        m.numeraires, m.fwd_factors, m.discounts = pnu, pff, pdi
+        m._keep = keep
+        return m
+
+    def european(self, strike):
+        p = cf_product()
+        p.kind, p.n_events, p.n_payoffs, p.strike = CF_PRODUCT_EUROPEAN, 1, 1, strike
+        return p
+
+    def uoc(self, strike, barrier, smooth_abs, n_events, is_put=False):
+        p = cf_product()
+        p.kind, p.n_events, p.n_payoffs, p.is_put = CF_PRODUCT_UOC, n_events, 2, int(is_put)
+        p.strike, p.barrier, p.smooth = strike, barrier, smooth_abs
+        return p
+
+    def run_value(self, mdl, prd, rng, first, n, per_path=False):
+        sums = np.zeros(prd.n_payoffs)
+        pp = np.zeros((n, prd.n_payoffs)) if per_path else None
+        self._chk(self.lib.cf_run_value(C.byref(mdl), C.byref(prd), C.byref(rng), first, n,
+                                        sums.ctypes.data_as(_dp), pp.ctypes.data_as(_dp) if per_path else None))
+        return (sums, pp) if per_path else sums
+
+    def run_aad(self, mdl, prd, rng, first, n, weights, per_path=False):
+        w, pw = self._d(weights)
+        sums = np.zeros(prd.n_payoffs)
+        agg = np.zeros(1)
+        nadj = self.lib.cf_table_adjoint_size(C.byref(mdl), C.byref(prd))
+        adj = np.zeros(nadj)
+        pp = np.zeros((n, prd.n_payoffs)) if per_path else None
+        pa = np.zeros(n) if per_path else None
+        self._chk(self.lib.cf_run_aad(C.byref(mdl), C.byref(prd), C.byref(rng), first, n, pw,
+                                      sums.ctypes.data_as(_dp), agg.ctypes.data_as(_dp), adj.ctypes.data_as(_dp),
+                                      pp.ctypes.data_as(_dp) if per_path else None,
+                                      pa.ctypes.data_as(_dp) if per_path else None))
+        out = dict(payoff_sums=sums, agg_sum=float(agg[0]), table_adj=adj)
+        if per_path:
+            out["payoffs"], out["agg"] = pp, pa
+        return out
+
+    def sobol_states(self, dim, first, n):
+        out = np.zeros((n, dim), dtype=np.uint32)
+        self._chk(self.lib.cf_sobol_states(dim, first, n, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def rng_draw(self, rng, dim, first, n, gaussian):
+        out = np.zeros((n, dim))
+        self._chk(self.lib.cf_rng_draw(C.byref(rng), dim, first, n, int(gaussian), out.ctypes.data_as(_dp)))
+        return out
+
+    def mrg_numerators(self, rng, dim, first, n):
+        out = np.zeros((n, dim), dtype=np.uint32)
+        self._chk(self.lib.cf_mrg_numerators(C.byref(rng), dim, first, n, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def inv_normal(self, p):
+        p, pp = self._d(p)
+        out = np.zeros_like(p)
+        self._chk(self.lib.cf_inv_normal(pp, out.ctypes.data_as(_dp), p.size))
+        return out
+
+    def direction_number(self, bit, dim):
+        return int(self.lib.cf_sobol_direction_number(bit, dim))

@@ -1,0 +1,550 @@
+// cf_api.cu -- the C ABI of include/cf_b200.h: context, resident plans, one-shot runs and the
+// RNG parity kernels.  No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/cf_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "cf_kernels.cuh"
+#include "cf_tables.h"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+int g_device = -1;
+int g_sms = 0;
+
+struct CfError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CF_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            throw CfError(std::string(#call) + ": " + cudaGetErrorString(e__));                    \
+    } while (0)
+
+template <class F>
+int guarded(F&& f)
+{
+    try { f(); return 0; }
+    catch (const std::exception& e) { g_err = e.what(); return 1; }
+    catch (...) { g_err = "unknown error"; return 1; }
+}
+
+void ensure_init()
+{
+    if (g_device >= 0) { CF_CUDA(cudaSetDevice(g_device)); return; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw CfError("cf_b200: no CUDA device available (this library has no CPU fallback)");
+    int dev = 0;
+    CF_CUDA(cudaGetDevice(&dev));
+    g_device = dev;
+    CF_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    void alloc(size_t count)
+    {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        if (count) CF_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    }
+    void upload(const T* src, size_t count, cudaStream_t s = nullptr)
+    {
+        alloc(count);
+        if (count) CF_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+};
+
+using KernelFn = void (*)(const cf::KArgs);
+
+template <int MDL, int PRD>
+KernelFn pick2(bool aad, int rng)
+{
+    if (aad) return rng == CF_RNG_SOBOL ? cf::path_kernel<MDL, PRD, true, CF_RNG_SOBOL>
+                                        : cf::path_kernel<MDL, PRD, true, CF_RNG_MRG32K3A>;
+    return rng == CF_RNG_SOBOL ? cf::path_kernel<MDL, PRD, false, CF_RNG_SOBOL>
+                               : cf::path_kernel<MDL, PRD, false, CF_RNG_MRG32K3A>;
+}
+
+KernelFn pick(int mdl, int prd, bool aad, int rng)
+{
+    if (mdl == CF_MODEL_BS && prd == CF_PRODUCT_EUROPEAN) return pick2<CF_MODEL_BS, CF_PRODUCT_EUROPEAN>(aad, rng);
+    if (mdl == CF_MODEL_BS && prd == CF_PRODUCT_UOC) return pick2<CF_MODEL_BS, CF_PRODUCT_UOC>(aad, rng);
+    if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_EUROPEAN) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_EUROPEAN>(aad, rng);
+    if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_UOC) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_UOC>(aad, rng);
+    throw CfError("cf_b200: model/product combination not implemented on the device");
+}
+
+size_t smem_for(int mdl, bool aad, int D, int m, int E, int dim, bool sobol)
+{
+    if (mdl == CF_MODEL_DUPIRE)
+        return aad ? cf::smem_bytes<CF_MODEL_DUPIRE, true>(D, m, E, dim, sobol)
+                   : cf::smem_bytes<CF_MODEL_DUPIRE, false>(D, m, E, dim, sobol);
+    return aad ? cf::smem_bytes<CF_MODEL_BS, true>(D, m, E, dim, sobol)
+               : cf::smem_bytes<CF_MODEL_BS, false>(D, m, E, dim, sobol);
+}
+
+size_t adj_size(const cf_model* mdl)
+{
+    if (mdl->kind == CF_MODEL_DUPIRE) return 1 + size_t(mdl->n_steps) * mdl->n_knots;
+    if (mdl->kind == CF_MODEL_BS) return 1 + 2 * size_t(mdl->n_steps) + 3 * size_t(mdl->n_events);
+    throw CfError("cf_b200: model kind not implemented");
+}
+
+void validate(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
+{
+    if (!mdl || !prd || !rng) throw CfError("cf_b200: null descriptor");
+    if (mdl->n_assets != 1) throw CfError("cf_b200: multi-asset models not implemented yet");
+    if (mdl->n_steps < 1 || mdl->n_events < 1) throw CfError("cf_b200: empty timeline");
+    if (mdl->n_events != prd->n_events) throw CfError("cf_b200: model and product disagree on the number of event dates");
+    if (!mdl->is_event) throw CfError("cf_b200: is_event missing");
+    int ev = 0;
+    for (int i = 0; i <= mdl->n_steps; ++i) ev += mdl->is_event[i] ? 1 : 0;
+    if (ev != mdl->n_events) throw CfError("cf_b200: is_event does not mark n_events points");
+    if (mdl->kind == CF_MODEL_DUPIRE) {
+        if (mdl->n_knots < 1 || !mdl->log_spots || !mdl->interp_vols) throw CfError("cf_b200: Dupire tables missing");
+        for (int j = 0; j + 1 < mdl->n_knots; ++j)
+            if (!(mdl->log_spots[j] < mdl->log_spots[j + 1])) throw CfError("cf_b200: Dupire spot knots must increase");
+    } else if (mdl->kind == CF_MODEL_BS) {
+        if (!mdl->bs_drifts || !mdl->bs_stds) throw CfError("cf_b200: Black-Scholes tables missing");
+        for (int i = 1; i <= mdl->n_steps; ++i)
+            if (!mdl->is_event[i]) throw CfError("cf_b200: every Black-Scholes step must end on an event date");
+    } else throw CfError("cf_b200: model kind not implemented");
+    if (prd->kind == CF_PRODUCT_EUROPEAN) { if (prd->n_payoffs != 1 || prd->n_events != 1) throw CfError("cf_b200: European has one event and one payoff"); }
+    else if (prd->kind == CF_PRODUCT_UOC) { if (prd->n_payoffs != 2) throw CfError("cf_b200: UOC has two payoffs"); if (!(prd->smooth > 0)) throw CfError("cf_b200: UOC smooth must be > 0"); }
+    else throw CfError("cf_b200: product kind not implemented");
+    if (rng->kind == CF_RNG_SOBOL) {
+        if (mdl->n_steps * mdl->n_assets > cf::sobol_max_dim()) throw CfError("cf_b200: Sobol dimension exceeds 1101");
+    } else if (rng->kind != CF_RNG_MRG32K3A) throw CfError("cf_b200: unknown RNG kind");
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct cf_plan {
+    int mdlKind = 0, prdKind = 0, rngKind = 0;
+    int D = 0, m = 0, E = 0, dim = 0, nPay = 0;
+    size_t nAdj = 0;           // table adjoints including the spot leaf
+    cf::KArgs base{};
+    DevBuf<uint8_t> isEvent;
+    DevBuf<double> tabA, tabB, num, ff, disc;
+    DevBuf<uint32_t> sobolDir;
+    DevBuf<uint64_t> mrgJump;
+    DevBuf<double> hist, partial;
+    int histGrid = 0, partialGrid = 0, partialStride = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // recorded since last query
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+
+    ~cf_plan()
+    {
+        for (auto& e : events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto& e : pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    }
+
+    size_t outSize(bool aad) const { return aad ? size_t(nPay) + 1 + nAdj : size_t(nPay); }
+
+    void launch(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut, double* dPerPath,
+                double* dPerAgg, cudaStream_t s)
+    {
+        if (n == 0) throw CfError("cf_b200: n_paths must be > 0");
+        if (rngKind == CF_RNG_SOBOL && first + n > 0xffffffffull) throw CfError("cf_b200: Sobol index exceeds 2^32 - 1");
+        const uint64_t nb64 = (n + cf::kBlock - 1) / cf::kBlock;
+        if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
+        const int nBatches = int(nb64);
+        const int grid = std::min(nBatches, 2 * g_sms);
+        const size_t stride = outSize(aad) + (aad ? 0 : 0);
+        if (partialGrid < grid || partialStride < int(stride)) {
+            partial.alloc(size_t(grid) * stride);
+            partialGrid = grid; partialStride = int(stride);
+        }
+        if (aad && histGrid < grid) {
+            hist.alloc(size_t(2) * D * size_t(grid) * cf::kBlock);
+            histGrid = grid;
+        }
+        cf::KArgs a = base;
+        a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
+        a.w[0] = a.w[1] = 0.0;
+        if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
+        a.partial = partial.p; a.partial_stride = partialStride;
+        a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg;
+        a.hist = hist.p;
+        KernelFn fn = pick(mdlKind, prdKind, aad, rngKind);
+        const size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL);
+        if (smem > 227 * 1024) throw CfError("cf_b200: tables do not fit in shared memory (n_steps * n_knots too large)");
+        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        std::pair<cudaEvent_t, cudaEvent_t> ev;
+        if (!pool.empty()) { ev = pool.back(); pool.pop_back(); }
+        else { CF_CUDA(cudaEventCreate(&ev.first)); CF_CUDA(cudaEventCreate(&ev.second)); }
+        CF_CUDA(cudaEventRecord(ev.first, s));
+        fn<<<grid, cf::kBlock, smem, s>>>(a);
+        CF_CUDA(cudaEventRecord(ev.second, s));
+        events.push_back(ev);
+        CF_CUDA(cudaGetLastError());
+        const int nOut = int(outSize(aad));
+        cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(partial.p, grid, partialStride, nOut, dOut);
+        CF_CUDA(cudaGetLastError());
+        g_launches += 2;
+    }
+};
+
+namespace {
+
+std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
+{
+    ensure_init();
+    validate(mdl, prd, rng);
+    auto p = std::make_unique<cf_plan>();
+    p->mdlKind = mdl->kind; p->prdKind = prd->kind; p->rngKind = rng->kind;
+    p->D = mdl->n_steps; p->E = mdl->n_events; p->dim = mdl->n_steps * mdl->n_assets;
+    p->m = mdl->kind == CF_MODEL_DUPIRE ? mdl->n_knots : 0;
+    p->nPay = prd->n_payoffs;
+    p->nAdj = adj_size(mdl);
+    p->isEvent.upload(mdl->is_event, size_t(p->D) + 1);
+    if (mdl->kind == CF_MODEL_DUPIRE) {
+        p->tabA.upload(mdl->interp_vols, size_t(p->D) * p->m);
+        p->tabB.upload(mdl->log_spots, size_t(p->m));
+    } else {
+        p->tabA.upload(mdl->bs_drifts, size_t(p->D));
+        p->tabB.upload(mdl->bs_stds, size_t(p->D));
+    }
+    if (mdl->numeraires) p->num.upload(mdl->numeraires, size_t(p->E));
+    if (mdl->fwd_factors) p->ff.upload(mdl->fwd_factors, size_t(p->E));
+    if (mdl->discounts) p->disc.upload(mdl->discounts, size_t(p->E));
+    if (rng->kind == CF_RNG_SOBOL) {
+        const auto& full = cf::sobol_direction_table();
+        const int nd = cf::sobol_max_dim();
+        std::vector<uint32_t> sub(size_t(32) * p->dim);
+        for (int b = 0; b < 32; ++b)
+            for (int d = 0; d < p->dim; ++d) sub[size_t(b) * p->dim + d] = full[size_t(b) * nd + d];
+        p->sobolDir.upload(sub.data(), sub.size());
+    } else {
+        const auto jump = cf::mrg_jump_matrices(uint64_t(p->dim));
+        p->mrgJump.upload(jump.data(), jump.size());
+    }
+    CF_CUDA(cudaStreamSynchronize(nullptr));   // staging vectors above go out of scope
+    cf::KArgs& a = p->base;
+    a.rng_kind = rng->kind; a.seed1 = rng->seed1; a.seed2 = rng->seed2; a.dim = p->dim;
+    a.sobol_dir = p->sobolDir.p; a.mrg_jump = p->mrgJump.p;
+    a.n_steps = p->D; a.n_events = p->E; a.n_knots = p->m;
+    a.is_event = p->isEvent.p; a.spot = mdl->spot;
+    a.tabA = p->tabA.p; a.tabB = p->tabB.p;
+    a.numeraires = p->num.p; a.fwd_factors = p->ff.p; a.discounts = p->disc.p;
+    a.n_payoffs = prd->n_payoffs; a.is_put = prd->is_put;
+    a.strike = prd->strike; a.barrier = prd->barrier; a.smooth = prd->smooth;
+    return p;
+}
+
+// ---- RNG parity kernels -----------------------------------------------------------------------
+__global__ void sobol_states_kernel(const uint32_t* __restrict__ dir, int dim, uint64_t first, uint64_t n,
+                                    uint32_t* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    uint32_t* dirlow = reinterpret_cast<uint32_t*>(raw);
+    uint32_t* base = dirlow + size_t(dim) * cf::kLowBits;
+    cf::sobol_load_low(dirlow, dir, dim);
+    const uint64_t nBatches = (n + cf::kBlock - 1) / cf::kBlock;
+    for (uint64_t batch = blockIdx.x; batch < nBatches; batch += gridDim.x) {
+        const uint32_t n0 = uint32_t(first + batch * cf::kBlock + 1);
+        const uint32_t H0 = n0 >> cf::kLowBits;
+        __syncthreads();
+        cf::sobol_block_base(base, dir, dim, H0);
+        __syncthreads();
+        const uint64_t p = batch * cf::kBlock + threadIdx.x;
+        cf::SobolThread st;
+        st.init(uint32_t(first + p + 1), H0);
+        if (p < n)
+            for (int d = 0; d < dim; ++d) out[p * dim + d] = st.state(dirlow, base, dim, d);
+    }
+}
+
+template <int RNGK>
+__global__ void rng_draw_kernel(const uint32_t* __restrict__ dir, const uint64_t* __restrict__ jump,
+                                uint32_t seed1, uint32_t seed2, int dim, uint64_t first, uint64_t n,
+                                int gaussian, double* __restrict__ out, uint32_t* __restrict__ outInt)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    uint32_t* dirlow = reinterpret_cast<uint32_t*>(raw);
+    uint32_t* base = dirlow + size_t(dim) * cf::kLowBits;
+    if (RNGK == CF_RNG_SOBOL) cf::sobol_load_low(dirlow, dir, dim);
+    const uint64_t nBatches = (n + cf::kBlock - 1) / cf::kBlock;
+    for (uint64_t batch = blockIdx.x; batch < nBatches; batch += gridDim.x) {
+        const uint64_t p = batch * cf::kBlock + threadIdx.x;
+        const uint64_t pabs = first + p;
+        cf::SobolThread st;
+        cf::MrgThread mrg;
+        if (RNGK == CF_RNG_SOBOL) {
+            const uint32_t n0 = uint32_t(first + batch * cf::kBlock + 1);
+            const uint32_t H0 = n0 >> cf::kLowBits;
+            __syncthreads();
+            cf::sobol_block_base(base, dir, dim, H0);
+            __syncthreads();
+            st.init(uint32_t(pabs + 1), H0);
+        } else {
+            mrg.init(seed1, seed2, pabs >> 1, jump);
+        }
+        if (p >= n) continue;
+        const bool odd = (pabs & 1ull) != 0;
+        for (int d = 0; d < dim; ++d) {
+            double u;
+            if (RNGK == CF_RNG_SOBOL) u = CF_ONEOVER2POW32 * double(st.state(dirlow, base, dim, d));
+            else {
+                const uint32_t z = mrg.next();
+                if (outInt) { outInt[p * dim + d] = z; continue; }
+                u = cf::mrg_uniform(z);
+            }
+            double r;
+            if (gaussian) { r = cf::inv_normal_cdf(u); if (RNGK != CF_RNG_SOBOL && odd) r = -r; }
+            else r = (RNGK != CF_RNG_SOBOL && odd) ? 1.0 - u : u;
+            out[p * dim + d] = r;
+        }
+    }
+}
+
+__global__ void inv_normal_kernel(const double* __restrict__ p, double* __restrict__ out, uint64_t n)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = cf::inv_normal_cdf(p[i]);
+}
+
+void rng_run(const cf_rng* rng, int dim, uint64_t first, uint64_t n, int gaussian, double* out, uint32_t* outInt,
+             bool statesOnly)
+{
+    ensure_init();
+    if (!rng) throw CfError("cf_b200: null rng");
+    if (dim < 1 || n == 0) throw CfError("cf_b200: empty request");
+    const bool sobol = rng->kind == CF_RNG_SOBOL;
+    if (sobol && dim > cf::sobol_max_dim()) throw CfError("cf_b200: Sobol dimension exceeds 1101");
+    if (sobol && first + n > 0xffffffffull) throw CfError("cf_b200: Sobol index exceeds 2^32 - 1");
+    DevBuf<uint32_t> dDir, dInt;
+    DevBuf<uint64_t> dJump;
+    DevBuf<double> dOut;
+    std::vector<uint32_t> sub;
+    std::vector<uint64_t> jump;
+    if (sobol) {
+        const auto& full = cf::sobol_direction_table();
+        const int nd = cf::sobol_max_dim();
+        sub.resize(size_t(32) * dim);
+        for (int b = 0; b < 32; ++b)
+            for (int d = 0; d < dim; ++d) sub[size_t(b) * dim + d] = full[size_t(b) * nd + d];
+        dDir.upload(sub.data(), sub.size());
+    } else {
+        jump = cf::mrg_jump_matrices(uint64_t(dim));
+        dJump.upload(jump.data(), jump.size());
+    }
+    if (out) dOut.alloc(n * dim);
+    if (outInt) dInt.alloc(n * dim);
+    const uint64_t nBatches = (n + cf::kBlock - 1) / cf::kBlock;
+    const int grid = int(std::min<uint64_t>(nBatches, uint64_t(8) * g_sms));
+    const size_t smem = sobol ? sizeof(uint32_t) * size_t(dim) * (cf::kLowBits + 2) : 0;
+    if (smem > 200 * 1024) throw CfError("cf_b200: dimension too large");
+    if (statesOnly) {
+        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(sobol_states_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        sobol_states_kernel<<<grid, cf::kBlock, smem>>>(dDir.p, dim, first, n, dInt.p);
+    } else if (sobol) {
+        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rng_draw_kernel<CF_RNG_SOBOL>), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        rng_draw_kernel<CF_RNG_SOBOL><<<grid, cf::kBlock, smem>>>(dDir.p, nullptr, 0, 0, dim, first, n, gaussian, dOut.p, nullptr);
+    } else {
+        rng_draw_kernel<CF_RNG_MRG32K3A><<<grid, cf::kBlock, 0>>>(nullptr, dJump.p, rng->seed1, rng->seed2, dim, first, n, gaussian, dOut.p, dInt.p);
+    }
+    ++g_launches;
+    CF_CUDA(cudaGetLastError());
+    if (out) CF_CUDA(cudaMemcpy(out, dOut.p, n * dim * sizeof(double), cudaMemcpyDeviceToHost));
+    if (outInt) CF_CUDA(cudaMemcpy(outInt, dInt.p, n * dim * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CF_CUDA(cudaDeviceSynchronize());
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* cf_last_error(void) { return g_err.c_str(); }
+uint64_t cf_launch_count(void) { return g_launches.load(); }
+
+int cf_init(int n_devices, const int* device_ids)
+{
+    return guarded([&] {
+        if (n_devices != 1 || !device_ids) throw CfError("cf_init: one process drives one GPU (n_devices must be 1)");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) throw CfError("cf_init: no CUDA device available (this library has no CPU fallback)");
+        if (device_ids[0] < 0 || device_ids[0] >= n) throw CfError("cf_init: device id out of range");
+        CF_CUDA(cudaSetDevice(device_ids[0]));
+        g_device = device_ids[0];
+        CF_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, g_device));
+        g_launches = 0;
+    });
+}
+
+int cf_shutdown(void)
+{
+    return guarded([&] {
+        if (g_device >= 0) CF_CUDA(cudaDeviceSynchronize());
+        g_device = -1;
+    });
+}
+
+size_t cf_table_adjoint_size(const cf_model* mdl, const cf_product* prd)
+{
+    (void)prd;
+    try { return mdl ? adj_size(mdl) : 0; } catch (const std::exception& e) { g_err = e.what(); return 0; }
+}
+
+int cf_plan_create(const cf_model* mdl, const cf_product* prd, const cf_rng* rng, cf_plan** out)
+{
+    return guarded([&] {
+        if (!out) throw CfError("cf_plan_create: null out");
+        *out = make_plan(mdl, prd, rng).release();
+    });
+}
+
+void cf_plan_destroy(cf_plan* plan) { delete plan; }
+
+size_t cf_plan_out_size(const cf_plan* plan, int aad) { return plan ? plan->outSize(aad != 0) : 0; }
+
+int cf_plan_launch_value(cf_plan* plan, uint64_t first_path, uint64_t n_paths, double* d_out, void* stream)
+{
+    return guarded([&] {
+        if (!plan || !d_out) throw CfError("cf_plan_launch_value: null argument");
+        ensure_init();
+        plan->launch(false, nullptr, first_path, n_paths, d_out, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int cf_plan_launch_aad(cf_plan* plan, const double* payoff_weights, uint64_t first_path, uint64_t n_paths,
+                       double* d_out, void* stream)
+{
+    return guarded([&] {
+        if (!plan || !d_out || !payoff_weights) throw CfError("cf_plan_launch_aad: null argument");
+        ensure_init();
+        plan->launch(true, payoff_weights, first_path, n_paths, d_out, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int cf_plan_kernel_ms(cf_plan* plan, double* avg_ms, int* n_launches)
+{
+    return guarded([&] {
+        if (!plan) throw CfError("cf_plan_kernel_ms: null plan");
+        double tot = 0.0;
+        int n = 0;
+        for (auto& ev : plan->events) {
+            CF_CUDA(cudaEventSynchronize(ev.second));
+            float ms = 0.f;
+            CF_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+            tot += ms; ++n;
+            plan->pool.push_back(ev);
+        }
+        plan->events.clear();
+        if (avg_ms) *avg_ms = n ? tot / n : 0.0;
+        if (n_launches) *n_launches = n;
+    });
+}
+
+int cf_run_value(const cf_model* mdl, const cf_product* prd, const cf_rng* rng, uint64_t first_path,
+                 uint64_t n_paths, double* payoff_sums, double* per_path_payoffs)
+{
+    return guarded([&] {
+        if (!payoff_sums) throw CfError("cf_run_value: payoff_sums is null");
+        auto plan = make_plan(mdl, prd, rng);
+        DevBuf<double> dOut, dPer;
+        dOut.alloc(plan->outSize(false));
+        if (per_path_payoffs) dPer.alloc(n_paths * plan->nPay);
+        plan->launch(false, nullptr, first_path, n_paths, dOut.p, dPer.p, nullptr, nullptr);
+        CF_CUDA(cudaMemcpy(payoff_sums, dOut.p, sizeof(double) * plan->nPay, cudaMemcpyDeviceToHost));
+        if (per_path_payoffs)
+            CF_CUDA(cudaMemcpy(per_path_payoffs, dPer.p, sizeof(double) * n_paths * plan->nPay, cudaMemcpyDeviceToHost));
+        CF_CUDA(cudaDeviceSynchronize());
+    });
+}
+
+int cf_run_aad(const cf_model* mdl, const cf_product* prd, const cf_rng* rng, uint64_t first_path,
+               uint64_t n_paths, const double* payoff_weights, double* payoff_sums, double* agg_sum,
+               double* table_adjoints, double* per_path_payoffs, double* per_path_agg)
+{
+    return guarded([&] {
+        if (!payoff_weights || !payoff_sums || !agg_sum || !table_adjoints) throw CfError("cf_run_aad: null output");
+        auto plan = make_plan(mdl, prd, rng);
+        DevBuf<double> dOut, dPer, dAgg;
+        const size_t nOut = plan->outSize(true);
+        dOut.alloc(nOut);
+        if (per_path_payoffs) dPer.alloc(n_paths * plan->nPay);
+        if (per_path_agg) dAgg.alloc(n_paths);
+        plan->launch(true, payoff_weights, first_path, n_paths, dOut.p, dPer.p, dAgg.p, nullptr);
+        std::vector<double> h(nOut);
+        CF_CUDA(cudaMemcpy(h.data(), dOut.p, sizeof(double) * nOut, cudaMemcpyDeviceToHost));
+        std::memcpy(payoff_sums, h.data(), sizeof(double) * plan->nPay);
+        *agg_sum = h[plan->nPay];
+        std::memcpy(table_adjoints, h.data() + plan->nPay + 1, sizeof(double) * plan->nAdj);
+        if (per_path_payoffs)
+            CF_CUDA(cudaMemcpy(per_path_payoffs, dPer.p, sizeof(double) * n_paths * plan->nPay, cudaMemcpyDeviceToHost));
+        if (per_path_agg) CF_CUDA(cudaMemcpy(per_path_agg, dAgg.p, sizeof(double) * n_paths, cudaMemcpyDeviceToHost));
+        CF_CUDA(cudaDeviceSynchronize());
+    });
+}
+
+int cf_sobol_states(int dim, uint64_t first_path, uint64_t n_paths, uint32_t* out)
+{
+    return guarded([&] {
+        if (!out) throw CfError("cf_sobol_states: null out");
+        cf_rng r{CF_RNG_SOBOL, 0, 0};
+        rng_run(&r, dim, first_path, n_paths, 0, nullptr, out, true);
+    });
+}
+
+uint32_t cf_sobol_direction_number(int bit, int dim)
+{
+    if (bit < 0 || bit >= 32 || dim < 0 || dim >= cf::sobol_max_dim()) return 0;
+    return cf::sobol_direction_table()[size_t(bit) * cf::sobol_max_dim() + dim];
+}
+
+int cf_sobol_max_dim(void) { return cf::sobol_max_dim(); }
+
+int cf_rng_draw(const cf_rng* rng, int dim, uint64_t first_path, uint64_t n_paths, int gaussian, double* out)
+{
+    return guarded([&] {
+        if (!out) throw CfError("cf_rng_draw: null out");
+        rng_run(rng, dim, first_path, n_paths, gaussian, out, nullptr, false);
+    });
+}
+
+int cf_mrg_numerators(const cf_rng* rng, int dim, uint64_t first_path, uint64_t n_paths, uint32_t* out)
+{
+    return guarded([&] {
+        if (!out || !rng || rng->kind != CF_RNG_MRG32K3A) throw CfError("cf_mrg_numerators: needs an mrg32k3a rng and out");
+        rng_run(rng, dim, first_path, n_paths, 0, nullptr, out, false);
+    });
+}
+
+int cf_inv_normal(const double* p, double* out, uint64_t n)
+{
+    return guarded([&] {
+        ensure_init();
+        if (!p || !out) throw CfError("cf_inv_normal: null argument");
+        if (n == 0) return;
+        DevBuf<double> dIn, dOut;
+        dIn.upload(p, n);
+        dOut.alloc(n);
+        inv_normal_kernel<<<unsigned((n + 255) / 256), 256>>>(dIn.p, dOut.p, n);
+        ++g_launches;
+        CF_CUDA(cudaGetLastError());
+        CF_CUDA(cudaMemcpy(out, dOut.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
+
+}  // extern "C"

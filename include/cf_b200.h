@@ -1,0 +1,182 @@
+/* cf_b200.h -- C ABI of the B200 Monte-Carlo path engine.
+ *
+ * Drop-in boundary for the data-parallel hot path of asavine/CompFinance: the six template
+ * algorithms of mcBase.h (mcSimul :267, mcParallelSimul :314, mcSimulAAD :429,
+ * mcParallelSimulAAD :566, mcSimulAADMulti :776, mcParallelSimulAADMulti :859) together with the
+ * RNG / model / product virtuals they call.  Everything that is path-INDEPENDENT (timelines,
+ * Model<T>::init tables, parameter chain rule = the part of the tape before tape.mark(),
+ * mcBase.h:559) stays on the host (compfinance_b200/host/ *.h mirrors the reference classes and
+ * flattens them into the POD structs below); everything O(paths) runs on the GPU.
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer, all functions return 0 on
+ * success and non-zero on failure with the message available from cf_last_error() (the C++ shim
+ * rethrows it as std::runtime_error, the reference's error convention, mcBase.h:273).
+ * There is NO CPU fallback: every entry point fails if no CUDA device is usable.
+ */
+#ifndef CF_B200_H
+#define CF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Random number generators (RNG interface, mcBase.h:228-246)
+ * ---------------------------------------------------------------------------------------- */
+enum { CF_RNG_SOBOL = 0,     /* sobol.h:31  (Joe-Kuo old 1111 direction numbers, Gray code) */
+       CF_RNG_MRG32K3A = 1   /* mrg32k3a.h:23 (L'Ecuyer, antithetic pairing) */ };
+
+typedef struct cf_rng {
+    int32_t  kind;
+    uint32_t seed1;   /* mrg32k3a a (default 12345), ignored by Sobol */
+    uint32_t seed2;   /* mrg32k3a b (default 12346) */
+} cf_rng;
+
+/* ------------------------------------------------------------------------------------------
+ * Models: flat image of what Model<T>::allocate/init leave behind (the "tables")
+ * ---------------------------------------------------------------------------------------- */
+enum { CF_MODEL_BS = 0,        /* mcMdlBS.h:25      */
+       CF_MODEL_DUPIRE = 1,    /* mcMdlDupire.h:28  */
+       CF_MODEL_DISPLACED = 2  /* mcMdlMultiDisplaced.h */ };
+
+typedef struct cf_model {
+    int32_t kind;
+    int32_t n_assets;      /* 1 for BS / Dupire */
+    int32_t n_steps;       /* time steps on the simulation timeline; simDim = n_steps * n_assets */
+    int32_t n_events;      /* size of the product timeline (samples per path) */
+    /* [n_steps + 1] 1 when simulation-timeline point i is an event date (Dupire myCommonSteps,
+     * mcMdlDupire.h:179-184; BS: point 0 = myTodayOnTimeline, all others 1). */
+    const uint8_t* is_event;
+
+    double spot;           /* single-asset S0 (parameter leaf) */
+
+    /* Black-Scholes tables, mcMdlBS.h:203-276 */
+    const double* bs_drifts;       /* [n_steps]  (mu -/+ vol^2/2) dt                 */
+    const double* bs_stds;         /* [n_steps]  vol sqrt(dt)                          */
+    /* Per event date, what the product's defline asks for (first forward / first discount only:
+     * every single-asset product of mcPrd.h in scope reads forwards[0][0], discounts[0], numeraire).
+     * NULL = the Sample defaults (numeraire 1, discount 1, forward factor 1; mcBase.h:91-99). */
+    const double* numeraires;      /* [n_events] */
+    const double* fwd_factors;     /* [n_events] */
+    const double* discounts;       /* [n_events] */
+
+    /* Dupire tables, mcMdlDupire.h:195-217 */
+    int32_t       n_knots;         /* spot knots of the local-vol surface */
+    const double* log_spots;       /* [n_knots] */
+    const double* interp_vols;     /* [n_steps][n_knots]  sqrt(dt_i) * vol(spot_j, t_i) */
+
+    /* Multi-asset displaced model tables, mcMdlMultiDisplaced.h:474-606 */
+    const double*  dlm_spots;      /* [n_assets] */
+    const double*  dlm_chol;       /* [n_assets][n_assets] lower */
+    const double*  dlm_alphas;     /* [n_assets] */
+    const int32_t* dlm_dynamics;   /* [n_assets] 0 lognormal 1 normal 2 surnormal 3 subnormal */
+    const double*  dlm_dyn_fwd;    /* [n_steps][n_assets] */
+    const double*  dlm_drifts;     /* [n_steps][n_assets] */
+    const double*  dlm_stds;       /* [n_steps][n_assets] */
+    const double*  dlm_fwd_factors;/* [n_events][n_assets] first forward maturity per asset */
+} cf_model;
+
+/* ------------------------------------------------------------------------------------------
+ * Products: constants of Product<T>::payoffs
+ * ---------------------------------------------------------------------------------------- */
+enum { CF_PRODUCT_EUROPEAN = 0,   /* mcPrd.h:29  */
+       CF_PRODUCT_UOC = 1,        /* mcPrd.h:128 */
+       CF_PRODUCT_EUROPEANS = 2,  /* mcPrd.h:290 */
+       CF_PRODUCT_BASKETS = 3,    /* mcPrdMulti.h:181 */
+       CF_PRODUCT_AUTOCALL = 4,   /* mcPrdMulti.h:289 */
+       CF_PRODUCT_MULTISTATS = 5  /* mcPrdMulti.h:11  */ };
+
+typedef struct cf_product {
+    int32_t kind;
+    int32_t n_events;
+    int32_t n_payoffs;
+    int32_t is_put;          /* UOC myCallPut */
+    double  strike;          /* European / UOC / Autocall */
+    double  barrier;         /* UOC barrier, Autocall KO */
+    double  smooth;          /* UOC: ABSOLUTE half-width double(S(t0) * smoothFactor), mcPrd.h:247;
+                                Autocall: max(smooth, EPS), mcPrdMulti.h:318 */
+    double  coupon;          /* Autocall */
+    /* Europeans: strikes of event e are strikes[strike_offsets[e] .. strike_offsets[e+1]) */
+    const int32_t* strike_offsets;  /* [n_events + 1] */
+    const double*  strikes;         /* Europeans / Baskets */
+    const double*  weights;         /* Baskets weights [n_assets]; Autocall refs [n_assets] */
+    const double*  event_dt;        /* Autocall: accrual period per event [n_events] */
+} cf_product;
+
+/* ------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------- */
+/* Bind this process to CUDA device device_ids[0] (one process per GPU; n_devices must be 1). */
+int cf_init(int n_devices, const int* device_ids);
+int cf_shutdown(void);
+const char* cf_last_error(void);
+/* Number of kernels launched by this library since cf_init (for bench accounting). */
+uint64_t cf_launch_count(void);
+
+/* Number of doubles in the table-adjoint vector of (model, product):
+ *   BS      : 1 (spot) + n_steps (drifts) + n_steps (stds) + 3 * n_events (numeraire, fwd factor, discount)
+ *   Dupire  : 1 (spot) + n_steps * n_knots (interp_vols, step-major)
+ *   Displaced: see cf_b200.h of later rounds (not implemented yet). */
+size_t cf_table_adjoint_size(const cf_model* mdl, const cf_product* prd);
+
+/* ------------------------------------------------------------------------------------------
+ * One-shot runs with HOST buffers (tables are uploaded, results downloaded inside the call)
+ * ---------------------------------------------------------------------------------------- */
+/* Replaces mcSimul / mcParallelSimul (mcBase.h:267, 314) for paths [first_path, first_path+n_paths).
+ *   payoff_sums     [n_payoffs]           sum over paths of each payoff (main.h:69-74 divides by N)
+ *   per_path_payoffs[n_paths][n_payoffs]  optional (NULL to skip): the reference's result matrix */
+int cf_run_value(const cf_model* mdl, const cf_product* prd, const cf_rng* rng,
+                 uint64_t first_path, uint64_t n_paths,
+                 double* payoff_sums, double* per_path_payoffs);
+
+/* Replaces mcSimulAAD / mcParallelSimulAAD (mcBase.h:429, 566) with the aggregator
+ * sum_k payoff_weights[k] * payoff[k] (main.h:135 and main.h:210-213 are both of this form).
+ *   payoff_sums     [n_payoffs]
+ *   agg_sum         [1]              sum over paths of the aggregate
+ *   table_adjoints  [cf_table_adjoint_size]  sum over paths of d aggregate / d table (NOT divided by N)
+ *   per_path_payoffs / per_path_agg optional */
+int cf_run_aad(const cf_model* mdl, const cf_product* prd, const cf_rng* rng,
+               uint64_t first_path, uint64_t n_paths, const double* payoff_weights,
+               double* payoff_sums, double* agg_sum, double* table_adjoints,
+               double* per_path_payoffs, double* per_path_agg);
+
+/* ------------------------------------------------------------------------------------------
+ * Resident plans: tables stay in HBM, results stay on the device (multi-GPU: the caller
+ * all-reduces d_out over NCCL and downloads once)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct cf_plan cf_plan;
+int  cf_plan_create(const cf_model* mdl, const cf_product* prd, const cf_rng* rng, cf_plan** out);
+void cf_plan_destroy(cf_plan* plan);
+/* d_out (device): [n_payoffs] payoff sums.  stream: cudaStream_t (NULL = default stream). */
+int cf_plan_launch_value(cf_plan* plan, uint64_t first_path, uint64_t n_paths, double* d_out, void* stream);
+/* d_out (device): [n_payoffs] payoff sums, [1] aggregate sum, [table_adjoint_size] adjoints. */
+int cf_plan_launch_aad(cf_plan* plan, const double* payoff_weights, uint64_t first_path, uint64_t n_paths,
+                       double* d_out, void* stream);
+size_t cf_plan_out_size(const cf_plan* plan, int aad);   /* doubles in d_out */
+/* Average duration in ms of the dominant (path) kernel over the launches since the last call
+ * (CUDA events recorded on the launch stream), and the number of launches averaged. */
+int cf_plan_kernel_ms(cf_plan* plan, double* avg_ms, int* n_launches);
+
+/* ------------------------------------------------------------------------------------------
+ * RNG kernels exposed for bit-exact parity tests (Sobol::next/skipTo sobol.h:77-151,
+ * mrg32k3a::nextNumber/skipTo mrg32k3a.h:55-81, 192-238, invNormalCdf gaussians.h:47-87)
+ * ---------------------------------------------------------------------------------------- */
+/* Sobol integer states of paths [first_path, first_path+n_paths): out[n_paths][dim] uint32 */
+int cf_sobol_states(int dim, uint64_t first_path, uint64_t n_paths, uint32_t* out);
+/* Direction number jkDir[bit][dim] regenerated from the Joe-Kuo initialisers (host, no GPU) */
+uint32_t cf_sobol_direction_number(int bit, int dim);
+int cf_sobol_max_dim(void);
+/* Uniforms (gaussian = 0) or Gaussians (gaussian = 1): out[n_paths][dim] doubles */
+int cf_rng_draw(const cf_rng* rng, int dim, uint64_t first_path, uint64_t n_paths, int gaussian, double* out);
+/* mrg32k3a integer numerators (x - y mod m1) of the stream positions used by the paths:
+ * out[n_paths][dim] uint32 (odd paths repeat their even partner, as the reference caches them) */
+int cf_mrg_numerators(const cf_rng* rng, int dim, uint64_t first_path, uint64_t n_paths, uint32_t* out);
+int cf_inv_normal(const double* p, double* out, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CF_B200_H */

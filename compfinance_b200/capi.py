@@ -80,7 +80,7 @@ EXPORTED = [
     "cf_init", "cf_shutdown", "cf_last_error", "cf_launch_count", "cf_table_adjoint_size", "cf_run_value",
     "cf_run_aad", "cf_plan_create", "cf_plan_destroy", "cf_plan_launch_value", "cf_plan_launch_aad",
     "cf_plan_out_size", "cf_plan_kernel_ms", "cf_sobol_states", "cf_sobol_direction_number", "cf_sobol_max_dim",
-    "cf_rng_draw", "cf_mrg_numerators", "cf_inv_normal",
+    "cf_rng_draw", "cf_mrg_numerators", "cf_inv_normal", "cf_measure_fp64_peak", "cf_device_sm_count",
 ]
 
 
@@ -193,6 +193,11 @@ class Engine:
         out = np.zeros_like(p)
         self._chk(self.lib.cf_inv_normal(pp, out.ctypes.data_as(_dp), p.size))
         return out
+
+    def fp64_peak_tflops(self):
+        t, ms = C.c_double(), C.c_double()
+        self._chk(self.lib.cf_measure_fp64_peak(C.byref(t), C.byref(ms)))
+        return t.value
 
     def direction_number(self, bit, dim):
         return int(self.lib.cf_sobol_direction_number(bit, dim))

@@ -2,7 +2,9 @@
 // RNG parity kernels.  No CPU fallback: every entry point needs a CUDA device.
 #include "../../include/cf_b200.h"
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -91,13 +93,13 @@ KernelFn pick(int mdl, int prd, bool aad, int rng)
     throw CfError("cf_b200: model/product combination not implemented on the device");
 }
 
-size_t smem_for(int mdl, bool aad, int D, int m, int E, int dim, bool sobol)
+size_t smem_for(int mdl, bool aad, int D, int m, int E, int dim, bool sobol, int lutN)
 {
     if (mdl == CF_MODEL_DUPIRE)
-        return aad ? cf::smem_bytes<CF_MODEL_DUPIRE, true>(D, m, E, dim, sobol)
-                   : cf::smem_bytes<CF_MODEL_DUPIRE, false>(D, m, E, dim, sobol);
-    return aad ? cf::smem_bytes<CF_MODEL_BS, true>(D, m, E, dim, sobol)
-               : cf::smem_bytes<CF_MODEL_BS, false>(D, m, E, dim, sobol);
+        return aad ? cf::smem_sizes<CF_MODEL_DUPIRE, true>(D, m, E, dim, sobol, lutN).total
+                   : cf::smem_sizes<CF_MODEL_DUPIRE, false>(D, m, E, dim, sobol, lutN).total;
+    return aad ? cf::smem_sizes<CF_MODEL_BS, true>(D, m, E, dim, sobol, lutN).total
+               : cf::smem_sizes<CF_MODEL_BS, false>(D, m, E, dim, sobol, lutN).total;
 }
 
 size_t adj_size(const cf_model* mdl)
@@ -146,6 +148,8 @@ struct cf_plan {
     DevBuf<double> tabA, tabB, num, ff, disc;
     DevBuf<uint32_t> sobolDir;
     DevBuf<uint64_t> mrgJump;
+    DevBuf<uint8_t> lut;
+    int lutN = 0, storeG = 1;
     DevBuf<double> hist, partial;
     int histGrid = 0, partialGrid = 0, partialStride = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // recorded since last query
@@ -174,7 +178,7 @@ struct cf_plan {
             partialGrid = grid; partialStride = int(stride);
         }
         if (aad && histGrid < grid) {
-            hist.alloc(size_t(2) * D * size_t(grid) * cf::kBlock);
+            hist.alloc(size_t(storeG ? 2 : 1) * D * size_t(grid) * cf::kBlock);
             histGrid = grid;
         }
         cf::KArgs a = base;
@@ -185,7 +189,7 @@ struct cf_plan {
         a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg;
         a.hist = hist.p;
         KernelFn fn = pick(mdlKind, prdKind, aad, rngKind);
-        const size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL);
+        const size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL, lutN);
         if (smem > 227 * 1024) throw CfError("cf_b200: tables do not fit in shared memory (n_steps * n_knots too large)");
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -223,6 +227,32 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
         p->tabA.upload(mdl->bs_drifts, size_t(p->D));
         p->tabB.upload(mdl->bs_stds, size_t(p->D));
     }
+    if (mdl->kind == CF_MODEL_DUPIRE) {
+        // Uniform-cell lookup for the spot bucket: cells no wider than half the smallest knot spacing,
+        // entry = number of knots <= left edge of the cell (capped by table size -> binary search).
+        const int m = p->m;
+        double minDx = 1e300, minVol = 1e300;
+        for (int j = 0; j + 1 < m; ++j) minDx = std::min(minDx, mdl->log_spots[j + 1] - mdl->log_spots[j]);
+        for (size_t i = 0; i < size_t(p->D) * m; ++i) minVol = std::min(minVol, std::fabs(mdl->interp_vols[i]));
+        p->storeG = minVol > 1.0e-6 ? 0 : 1;   // g - v is recovered from log-spot increments unless some vol ~ 0
+        const double range = m > 1 ? mdl->log_spots[m - 1] - mdl->log_spots[0] : 0.0;
+        if (m > 1 && m < 255 && range / minDx * 2.0 + 2.0 <= 8192.0) {
+            const int n = int(std::ceil(range / minDx * 2.0)) + 1;
+            const double scale = double(n) / range;   // cell width = range / n <= minDx / 2
+            std::vector<uint8_t> lut(size_t(n) + 1);
+            for (int c = 0; c <= n; ++c) {
+                const double edge = mdl->log_spots[0] + double(c) / scale;
+                int ub = 0;
+                while (ub < m && mdl->log_spots[ub] <= edge) ++ub;
+                lut[size_t(c)] = uint8_t(ub);
+            }
+            p->lutN = n + 1;
+            p->lut.upload(lut.data(), lut.size());
+            CF_CUDA(cudaStreamSynchronize(nullptr));
+            p->base.lut_x0 = mdl->log_spots[0];
+            p->base.lut_scale = scale;
+        }
+    }
     if (mdl->numeraires) p->num.upload(mdl->numeraires, size_t(p->E));
     if (mdl->fwd_factors) p->ff.upload(mdl->fwd_factors, size_t(p->E));
     if (mdl->discounts) p->disc.upload(mdl->discounts, size_t(p->E));
@@ -239,12 +269,13 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     }
     CF_CUDA(cudaStreamSynchronize(nullptr));   // staging vectors above go out of scope
     cf::KArgs& a = p->base;
-    a.rng_kind = rng->kind; a.seed1 = rng->seed1; a.seed2 = rng->seed2; a.dim = p->dim;
+    a.seed1 = rng->seed1; a.seed2 = rng->seed2; a.dim = p->dim;
     a.sobol_dir = p->sobolDir.p; a.mrg_jump = p->mrgJump.p;
     a.n_steps = p->D; a.n_events = p->E; a.n_knots = p->m;
     a.is_event = p->isEvent.p; a.spot = mdl->spot;
     a.tabA = p->tabA.p; a.tabB = p->tabB.p;
     a.numeraires = p->num.p; a.fwd_factors = p->ff.p; a.discounts = p->disc.p;
+    a.lut = p->lut.p; a.lut_n = p->lutN; a.store_g = p->storeG;
     a.n_payoffs = prd->n_payoffs; a.is_put = prd->is_put;
     a.strike = prd->strike; a.barrier = prd->barrier; a.smooth = prd->smooth;
     return p;
@@ -320,6 +351,19 @@ __global__ void inv_normal_kernel(const double* __restrict__ p, double* __restri
 {
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = cf::inv_normal_cdf(p[i]);
+}
+
+
+// FP64 peak microbenchmark: 8 independent DFMA chains per thread (roofline denominator of bench.py)
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;
 }
 
 void rng_run(const cf_rng* rng, int dim, uint64_t first, uint64_t n, int gaussian, double* out, uint32_t* outInt,
@@ -530,6 +574,35 @@ int cf_mrg_numerators(const cf_rng* rng, int dim, uint64_t first_path, uint64_t 
         rng_run(rng, dim, first_path, n_paths, 0, nullptr, out, false);
     });
 }
+
+
+int cf_measure_fp64_peak(double* tflops, double* ms_out)
+{
+    return guarded([&] {
+        ensure_init();
+        DevBuf<double> d; d.alloc(1);
+        const int iters = 1 << 14, grid = g_sms * 8, block = 256;
+        cudaEvent_t e0, e1;
+        CF_CUDA(cudaEventCreate(&e0)); CF_CUDA(cudaEventCreate(&e1));
+        double best = 1e30;
+        for (int rep = 0; rep < 5; ++rep) {
+            CF_CUDA(cudaEventRecord(e0));
+            fp64_peak_kernel<<<grid, block>>>(d.p, iters, 0.999999, 1e-7);
+            CF_CUDA(cudaEventRecord(e1));
+            CF_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+            ++g_launches;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        const double flops = double(grid) * block * 8.0 * iters * 2.0;
+        if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+        if (ms_out) *ms_out = best;
+    });
+}
+
+int cf_device_sm_count(void) { try { ensure_init(); return g_sms; } catch (const std::exception& e) { g_err = e.what(); return -1; } }
 
 int cf_inv_normal(const double* p, double* out, uint64_t n)
 {

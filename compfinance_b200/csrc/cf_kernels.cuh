@@ -8,6 +8,16 @@
 // mcMdlDupire.h:238-280, BlackScholes::generatePath mcMdlBS.h:321-350, European::payoffs
 // mcPrd.h:113-125, UOC::payoffs mcPrd.h:235-288, and the tape (AADTape.h / AADExpr.h) on that path.
 // Adjoint equations: SURVEY.md Appendix A.1 / A.2.
+//
+// Performance structure (B200, FP64-pipe bound):
+//  * Gaussians are produced a chunk of kChunk steps at a time per warp; the rare, expensive tail
+//    branch of the Moro inverse (log(-log u), 16 % of draws) is compacted across the chunk so the
+//    warp pays ~2-3 dense passes per chunk instead of one divergent pass per step.
+//  * The spot bucket of the local-vol row is found with a uniform-cell lookup table + one
+//    correcting compare instead of a binary search (bit-identical bucket to std::upper_bound).
+//  * Barrier tests are done in log space; exp() is evaluated only on the final date and on the
+//    rare samples inside the smoothing zone, where the reference's own comparisons are replayed.
+//  * The reverse sweep stores only log-spots: g_i - v_i is recovered from consecutive log-spots.
 #pragma once
 
 #include "cf_device.cuh"
@@ -15,16 +25,15 @@
 
 namespace cf {
 
-constexpr int kMaxPay = 2;   // payoffs held per thread (European: 1, UOC: 2)
+constexpr int kMaxPay = 2;    // payoffs held per thread (European: 1, UOC: 2)
+constexpr int kChunk = 8;     // steps of Gaussians staged per warp
 
-// Kernel arguments: device pointers to the uploaded tables (see cf_model / cf_product).
 struct KArgs {
     // run
     uint64_t first_path;
     uint64_t n_paths;
     int      n_batches;
     // rng
-    int      rng_kind;
     uint32_t seed1, seed2;
     int      dim;                  // = n_steps (single asset)
     const uint32_t* sobol_dir;     // [32][dim]
@@ -35,9 +44,14 @@ struct KArgs {
     double   spot;
     const double* tabA;            // BS: drifts [n_steps]      Dupire: interp_vols [n_steps][n_knots]
     const double* tabB;            // BS: stds   [n_steps]      Dupire: log_spots [n_knots]
-    const double* numeraires;      // [n_events] or null
+    const double* numeraires;      // [n_events] or null (BS only; Dupire leaves the Sample defaults)
     const double* fwd_factors;     // [n_events] or null
     const double* discounts;       // [n_events] or null
+    // Dupire bucket lookup: cell = (L - lut_x0) * lut_scale, lut[cell] = #knots <= left edge of cell
+    const uint8_t* lut;
+    int      lut_n;                // 0 = no table, use binary search
+    double   lut_x0, lut_scale;
+    int      store_g;              // 1: keep g_i in the history (needed when some interp_vol ~ 0)
     // product
     int      n_payoffs, is_put;
     double   strike, barrier, smooth;
@@ -48,65 +62,92 @@ struct KArgs {
     double*  per_path_payoffs;     // [n_paths][n_payoffs] or null
     double*  per_path_agg;         // [n_paths] or null
     // scratch
-    double*  hist;                 // [2][n_steps][gridDim * kBlock]
+    double*  hist;                 // [1 or 2][n_steps][gridDim * kBlock]
 };
+
+// ---------------------------------------------------------------------------------------------
+// Spot sources handed to the products.  Dupire carries the log-spot and evaluates exp lazily;
+// Black-Scholes carries the forward itself.
+// ---------------------------------------------------------------------------------------------
+struct LogSpotSrc {      // Dupire: forwards[0][0] = spot = exp(L), numeraire = discount = 1
+    static constexpr bool kHasLog = true;
+    double L, S;
+    bool have;
+    __device__ explicit LogSpotSrc(double l) : L(l), S(0.0), have(false) {}
+    __device__ double logFwd() const { return L; }
+    __device__ double fwd() { if (!have) { S = exp(L); have = true; } return S; }
+    __device__ double num() const { return 1.0; }
+    __device__ double disc() const { return 1.0; }
+};
+struct FwdSrc {          // Black-Scholes: forward = S * ff[e], numeraire / discount from tables
+    static constexpr bool kHasLog = false;
+    double F, N, Dsc;
+    __device__ FwdSrc(double f, double n, double d) : F(f), N(n), Dsc(d) {}
+    __device__ double logFwd() const { return 0.0; }
+    __device__ double fwd() { return F; }
+    __device__ double num() const { return N; }
+    __device__ double disc() const { return Dsc; }
+};
+struct SampleAdj { double fwd, num, disc; };
 
 // ---------------------------------------------------------------------------------------------
 // Products (streaming form: one call per event date, in order)
 // ---------------------------------------------------------------------------------------------
-struct Sample { double fwd, num, disc; };   // forwards[0][0], numeraire, discounts[0]
-struct SampleAdj { double fwd, num, disc; };
-
 template <int PRD> struct Product;
 
 // European call, mcPrd.h:113-125: payoff = max(F - K, 0) * disc / num at the single event date
 template <> struct Product<CF_PRODUCT_EUROPEAN> {
-    double strike, pay;
+    double strike, pay, wbar;
     __device__ void init(const KArgs& a) { strike = a.strike; pay = 0.0; }
-    __device__ void observe(int e, int nEvents, const Sample& s)
+    template <class Src> __device__ void observe(int e, int nEvents, Src& s)
     {
-        if (e == 0) pay = fmax(s.fwd - strike, 0.0) * s.disc / s.num;
+        if (e == 0) pay = fmax(s.fwd() - strike, 0.0) * s.disc() / s.num();
     }
     __device__ void payoffs(double* out) const { out[0] = pay; }
-    // reverse: agg = w[0] * pay
     __device__ void begin_reverse(const double* w) { wbar = w[0]; }
-    __device__ SampleAdj reverse(int e, int nEvents, const Sample& s) const
+    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s)
     {
         SampleAdj r = {0.0, 0.0, 0.0};
         if (e == 0) {
-            const double intrinsic = fmax(s.fwd - strike, 0.0);
+            const double F = s.fwd();
+            const double intrinsic = fmax(F - strike, 0.0);
             // max(x, 0) has derivative 1 iff x > 0 strictly (AADExpr.h:571-583)
-            r.fwd = (s.fwd - strike > 0.0) ? wbar * s.disc / s.num : 0.0;
-            r.disc = wbar * intrinsic / s.num;
-            r.num = -wbar * intrinsic * s.disc / s.num / s.num;
+            r.fwd = (F - strike > 0.0) ? wbar * s.disc() / s.num() : 0.0;
+            r.disc = wbar * intrinsic / s.num();
+            r.num = -wbar * intrinsic * s.disc() / s.num() / s.num();
         }
         return r;
     }
-    double wbar;
 };
 
 // Up-and-out call/put with smoothed barrier, mcPrd.h:235-288.
 template <> struct Product<CF_PRODUCT_UOC> {
-    double strike, barSmooth, minusSmooth, twoSmooth;
+    double strike, barSmooth, minusSmooth, twoSmooth, logZone;
     double alive, euro;
     bool   killed, isPut;
-    // reverse state
-    double abar, aliveCur, eurobar;
+    double abar, aliveCur, eurobar;     // reverse state
 
     __device__ void init(const KArgs& a)
     {
         strike = a.strike; isPut = a.is_put != 0;
         twoSmooth = 2 * a.smooth; barSmooth = a.barrier + a.smooth; minusSmooth = a.barrier - a.smooth;
+        // log-space pre-filter: below this log-forward the sample is certainly outside the smoothing
+        // zone (margin >> rounding of exp/log); at or above it the reference's comparisons are
+        // replayed on the forward itself.
+        logZone = minusSmooth > 0.0 ? log(minusSmooth) - 1.0e-9 : -1.0e300;
         alive = 1.0; euro = 0.0; killed = false;
     }
-    __device__ void observe(int e, int nEvents, const Sample& s)
+    template <class Src> __device__ void observe(int e, int nEvents, Src& s)
     {
-        if (!killed) {
-            if (s.fwd > barSmooth) { killed = true; alive = 0.0; }
-            else if (s.fwd > minusSmooth) alive *= (barSmooth - s.fwd) / twoSmooth;
+        if (!killed && (!Src::kHasLog || s.logFwd() > logZone)) {
+            const double F = s.fwd();
+            if (F > barSmooth) { killed = true; alive = 0.0; }
+            else if (F > minusSmooth) alive *= (barSmooth - F) / twoSmooth;
         }
-        if (e == nEvents - 1)
-            euro = (isPut ? fmax(strike - s.fwd, 0.0) : fmax(s.fwd - strike, 0.0)) / s.num;
+        if (e == nEvents - 1) {
+            const double F = s.fwd();
+            euro = (isPut ? fmax(strike - F, 0.0) : fmax(F - strike, 0.0)) / s.num();
+        }
     }
     __device__ void payoffs(double* out) const { out[0] = alive * euro; out[1] = euro; }
 
@@ -116,21 +157,25 @@ template <> struct Product<CF_PRODUCT_UOC> {
         abar = killed ? 0.0 : w[0] * euro;      // a killed `alive` is a fresh leaf: nothing flows
         aliveCur = alive;
     }
-    __device__ SampleAdj reverse(int e, int nEvents, const Sample& s)
+    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s)
     {
         SampleAdj r = {0.0, 0.0, 0.0};
         if (e == nEvents - 1) {
-            const double x = isPut ? strike - s.fwd : s.fwd - strike;
-            if (x > 0.0) r.fwd = (isPut ? -eurobar : eurobar) / s.num;
-            r.num = -eurobar * euro / s.num;
+            const double F = s.fwd();
+            const double x = isPut ? strike - F : F - strike;
+            if (x > 0.0) r.fwd = (isPut ? -eurobar : eurobar) / s.num();
+            r.num = -eurobar * euro / s.num();
         }
-        if (!killed && s.fwd > minusSmooth) {   // fuzzy sample (s.fwd <= barSmooth on a live path)
-            const double f = (barSmooth - s.fwd) / twoSmooth;
-            // alive before this sample; f == 0 only if the spot sits exactly on the upper edge
-            const double alivePrev = (f != 0.0) ? aliveCur / f : 0.0;
-            r.fwd += abar * alivePrev * (-1.0 / twoSmooth);
-            abar *= f;
-            aliveCur = alivePrev;
+        if (!killed && (!Src::kHasLog || s.logFwd() > logZone)) {
+            const double F = s.fwd();
+            if (F > minusSmooth) {              // fuzzy sample (F <= barSmooth on a live path)
+                const double f = (barSmooth - F) / twoSmooth;
+                // alive before this sample; f == 0 only if the spot sits exactly on the upper edge
+                const double alivePrev = (f != 0.0) ? aliveCur / f : 0.0;
+                r.fwd += abar * alivePrev * (-1.0 / twoSmooth);
+                abar *= f;
+                aliveCur = alivePrev;
+            }
         }
         return r;
     }
@@ -146,8 +191,12 @@ struct Smem {
     double*   adj;       // block table adjoints (AAD)
     double2*  wrow;      // [2][kWarps][rowlen] warp rows (AAD)
     double*   red;       // [kWarps] reduction scratch
+    double*   gq;        // [kWarps][kChunk][32] staged Gaussians
+    uint16_t* tagq;      // [kWarps][kChunk*32] tail queue
     uint32_t* dirlow;    // [dim][8]
     uint32_t* base;      // [2][dim]
+    uint8_t*  lut;       // [lut_n]
+    uint8_t*  isev;      // [n_steps + 1]
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -156,7 +205,6 @@ template <int MDL>
 __host__ __device__ inline int table_a_size(int nSteps, int nKnots) { return MDL == CF_MODEL_DUPIRE ? nSteps * nKnots : nSteps; }
 template <int MDL>
 __host__ __device__ inline int table_b_size(int nSteps, int nKnots) { return MDL == CF_MODEL_DUPIRE ? nKnots : nSteps; }
-// adjoint slots accumulated through the per-step block table
 template <int MDL>
 __host__ __device__ inline int adj_table_size(int nSteps, int nKnots, int nEvents)
 {
@@ -165,71 +213,153 @@ __host__ __device__ inline int adj_table_size(int nSteps, int nKnots, int nEvent
 template <int MDL>
 __host__ __device__ inline int row_len(int nKnots) { return MDL == CF_MODEL_DUPIRE ? (nKnots > 1 ? nKnots - 1 : 1) : 3; }
 
+struct SmemSizes { size_t tabA, tabB, invdx, adj, wrow, red, gq, tagq, dirlow, base, lut, isev, total; };
+
 template <int MDL, bool AAD>
-__host__ __device__ inline size_t smem_bytes(int nSteps, int nKnots, int nEvents, int dim, bool sobol)
+__host__ __device__ inline SmemSizes smem_sizes(int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN)
 {
-    size_t s = 0;
-    s += align16(sizeof(double) * table_a_size<MDL>(nSteps, nKnots));
-    s += align16(sizeof(double) * table_b_size<MDL>(nSteps, nKnots));
-    s += align16(sizeof(double) * (nKnots > 0 ? nKnots : 1));
-    if (AAD) {
-        s += align16(sizeof(double) * adj_table_size<MDL>(nSteps, nKnots, nEvents));
-        s += align16(sizeof(double2) * 2 * kWarps * row_len<MDL>(nKnots));
-    }
-    s += align16(sizeof(double) * kWarps);
-    if (sobol) {
-        s += align16(sizeof(uint32_t) * dim * kLowBits);
-        s += align16(sizeof(uint32_t) * 2 * dim);
-    }
+    SmemSizes s{};
+    s.tabA = align16(sizeof(double) * table_a_size<MDL>(nSteps, nKnots));
+    s.tabB = align16(sizeof(double) * table_b_size<MDL>(nSteps, nKnots));
+    s.invdx = align16(sizeof(double) * (nKnots > 0 ? nKnots : 1));
+    s.adj = AAD ? align16(sizeof(double) * adj_table_size<MDL>(nSteps, nKnots, nEvents)) : 0;
+    s.wrow = AAD ? align16(sizeof(double2) * 2 * kWarps * row_len<MDL>(nKnots)) : 0;
+    s.red = align16(sizeof(double) * kWarps);
+    s.gq = align16(sizeof(double) * kWarps * kChunk * 32);
+    s.tagq = align16(sizeof(uint16_t) * kWarps * kChunk * 32);
+    s.dirlow = sobol ? align16(sizeof(uint32_t) * dim * kLowBits) : 0;
+    s.base = sobol ? align16(sizeof(uint32_t) * 2 * dim) : 0;
+    s.lut = align16(size_t(lutN > 0 ? lutN : 1));
+    s.isev = align16(size_t(nSteps) + 1);
+    // wrow (reverse sweep) aliases gq + tagq (forward sweep): the two phases never overlap within a block
+    if (s.gq + s.tagq < s.wrow) s.gq = s.wrow - s.tagq;
+    s.total = s.tabA + s.tabB + s.invdx + s.adj + s.red + s.gq + s.tagq + s.dirlow + s.base + s.lut + s.isev;
     return s;
 }
 
 template <int MDL, bool AAD>
-__device__ inline Smem carve(unsigned char* p, int nSteps, int nKnots, int nEvents, int dim, bool sobol)
+__device__ inline Smem carve(unsigned char* p, int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN)
 {
+    const SmemSizes z = smem_sizes<MDL, AAD>(nSteps, nKnots, nEvents, dim, sobol, lutN);
     Smem s{};
-    s.tabA = reinterpret_cast<double*>(p);  p += align16(sizeof(double) * table_a_size<MDL>(nSteps, nKnots));
-    s.tabB = reinterpret_cast<double*>(p);  p += align16(sizeof(double) * table_b_size<MDL>(nSteps, nKnots));
-    s.invdx = reinterpret_cast<double*>(p); p += align16(sizeof(double) * (nKnots > 0 ? nKnots : 1));
-    if (AAD) {
-        s.adj = reinterpret_cast<double*>(p);   p += align16(sizeof(double) * adj_table_size<MDL>(nSteps, nKnots, nEvents));
-        s.wrow = reinterpret_cast<double2*>(p); p += align16(sizeof(double2) * 2 * kWarps * row_len<MDL>(nKnots));
-    }
-    s.red = reinterpret_cast<double*>(p);   p += align16(sizeof(double) * kWarps);
-    if (sobol) {
-        s.dirlow = reinterpret_cast<uint32_t*>(p); p += align16(sizeof(uint32_t) * dim * kLowBits);
-        s.base = reinterpret_cast<uint32_t*>(p);
-    }
+    s.tabA = reinterpret_cast<double*>(p);    p += z.tabA;
+    s.tabB = reinterpret_cast<double*>(p);    p += z.tabB;
+    s.invdx = reinterpret_cast<double*>(p);   p += z.invdx;
+    s.adj = reinterpret_cast<double*>(p);     p += z.adj;
+    s.wrow = reinterpret_cast<double2*>(p + z.red);   // aliases gq / tagq
+    s.red = reinterpret_cast<double*>(p);     p += z.red;
+    s.gq = reinterpret_cast<double*>(p);      p += z.gq;
+    s.tagq = reinterpret_cast<uint16_t*>(p);  p += z.tagq;
+    s.dirlow = reinterpret_cast<uint32_t*>(p); p += z.dirlow;
+    s.base = reinterpret_cast<uint32_t*>(p);  p += z.base;
+    s.lut = reinterpret_cast<uint8_t*>(p);    p += z.lut;
+    s.isev = reinterpret_cast<uint8_t*>(p);
     return s;
 }
 
 // ---------------------------------------------------------------------------------------------
 // interp (interp.h:26-63) on the smem row y against knots x: upper_bound, flat extrapolation.
-// Returns v; n = left knot of the bucket, t = weight of knot n+1, slope = dv/dx0 (0 when flat).
 // ---------------------------------------------------------------------------------------------
-struct Interp { double v, t, slope; int n; };
+struct Bucket { int n; int side; };   // left knot of the bucket; side: 0 inside, -1 / +1 flat extrapolation left / right
 
-__device__ __forceinline__ Interp interp_row(const double* __restrict__ x, const double* __restrict__ invdx,
-                                            const double* __restrict__ y, int m, int p2, double x0)
-{
-    // ub = number of knots <= x0  (std::upper_bound)
-    int ub = 0;
-    for (int s = p2; s > 0; s >>= 1) {
-        const int c = ub + s;
-        if (c <= m && x[c - 1] <= x0) ub = c;
+struct Locator {
+    const double* x; const uint8_t* lut;
+    int m, p2, lutN;
+    double x0, scale;
+
+    // ub = number of knots <= v  (std::upper_bound)
+    __device__ __forceinline__ int upper_bound(double v) const
+    {
+        int ub;
+        if (lutN > 0) {
+            // uniform cells of width <= half the smallest knot spacing: the cell's entry is within
+            // one of the answer, one compare each way settles it
+            double c = (v - x0) * scale;
+            c = fmin(fmax(c, 0.0), double(lutN - 1));
+            ub = lut[__double2int_rz(c)];
+            if (ub < m && x[ub] <= v) ++ub;
+            else if (ub > 0 && x[ub - 1] > v) --ub;
+        } else {
+            ub = 0;
+            for (int s = p2; s > 0; s >>= 1) {
+                const int c = ub + s;
+                if (c <= m && x[c - 1] <= v) ub = c;
+            }
+        }
+        return ub;
     }
-    Interp r;
-    if (ub == m) { r.n = (m > 1 ? m - 2 : 0); r.t = (m > 1 ? 1.0 : 0.0); r.v = y[m - 1]; r.slope = 0.0; }
-    else if (ub == 0) { r.n = 0; r.t = 0.0; r.v = y[0]; r.slope = 0.0; }
-    else {
-        const int n = ub - 1;
-        const double y1 = y[n], y2 = y[n + 1];
-        const double t = (x0 - x[n]) * invdx[n];
-        r.n = n; r.t = t; r.slope = (y2 - y1) * invdx[n];
-        r.v = y1 + (y2 - y1) * t;
+    __device__ __forceinline__ Bucket locate(double v) const
+    {
+        const int ub = upper_bound(v);
+        Bucket b;
+        if (ub == m) { b.n = m > 1 ? m - 2 : 0; b.side = 1; }
+        else if (ub == 0) { b.n = 0; b.side = -1; }
+        else { b.n = ub - 1; b.side = 0; }
+        return b;
     }
-    return r;
-}
+};
+
+// ---------------------------------------------------------------------------------------------
+// Gaussians for a chunk of steps, per warp (all lanes must call together).
+// Central branch of invNormalCdf (gaussians.h:73-78) inline; tail branch (80-86) compacted.
+// ---------------------------------------------------------------------------------------------
+template <int RNGK>
+struct GaussGen {
+    SobolThread sob;
+    MrgThread   mrg;
+    double      sign;        // mrg32k3a antithetic: -1 on odd paths
+    double*     gq;          // this warp's [kChunk][32]
+    uint16_t*   tagq;        // this warp's [kChunk*32]
+    const uint32_t* dirlow; const uint32_t* base; int dim;
+
+    __device__ __forceinline__ double uniform(int d)
+    {
+        if (RNGK == CF_RNG_SOBOL) return CF_ONEOVER2POW32 * double(sob.state(dirlow, base, dim, d));
+        return mrg_uniform(mrg.next());
+    }
+
+    __device__ __forceinline__ void fill(int i0, int cnt)
+    {
+        const int lane = threadIdx.x & 31;
+        const unsigned ltMask = (1u << lane) - 1u;
+        int q = 0;
+        __syncwarp();
+        for (int k = 0; k < cnt; ++k) {
+            const double p = uniform(i0 + k);
+            const bool sup = p > 0.5;
+            const double up = sup ? 1.0 - p : p;
+            const double x = up - 0.5;
+            const bool central = fabs(x) < 0.42;
+            double r = x * x;
+            const double num = ((-25.44106049637 * r + 41.39119773534) * r + -18.61500062529) * r + 2.50662823884;
+            const double den = (((3.13082909833 * r + -21.06224101826) * r + 23.08336743743) * r + -8.47351093090) * r + 1.0;
+            r = x * num / den;
+            gq[k * 32 + lane] = central ? (sup ? -r : r) : up;
+            const unsigned ball = __ballot_sync(kFull, !central);
+            if (!central) tagq[q + __popc(ball & ltMask)] = uint16_t((sup ? 0x8000u : 0u) | (unsigned(k) << 5) | unsigned(lane));
+            q += __popc(ball);
+        }
+        __syncwarp();
+        for (int b = 0; b < q; b += 32) {
+            const int idx = b + lane;
+            if (idx < q) {
+                const unsigned t = tagq[idx];
+                const int slot = int(t & 0x7fffu);            // k * 32 + lane
+                double r = log(-log(gq[slot]));
+                r = 0.3374754822726147 + r * (0.9761690190917186 + r * (0.1607979714918209 + r * (0.0276438810333863
+                    + r * (0.0038405729373609 + r * (0.0003951896511919 + r * (0.0000321767881768
+                    + r * (0.0000002888167364 + r * 0.0000003960315187)))))));
+                gq[slot] = (t & 0x8000u) ? r : -r;
+            }
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ double get(int k) const
+    {
+        const double g = gq[k * 32 + (threadIdx.x & 31)];
+        return RNGK == CF_RNG_SOBOL ? g : sign * g;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // The path kernel
@@ -241,29 +371,41 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = a.n_steps, m = a.n_knots, E = a.n_events;
     constexpr bool kSobol = (RNGK == CF_RNG_SOBOL);
-    const Smem sm = carve<MDL, AAD>(smem_raw, D, m, E, a.dim, kSobol);
+    constexpr bool kDupire = (MDL == CF_MODEL_DUPIRE);
+    const Smem sm = carve<MDL, AAD>(smem_raw, D, m, E, a.dim, kSobol, a.lut_n);
     const int rowLen = row_len<MDL>(m);
     const int nAdj = adj_table_size<MDL>(D, m, E);
+    const bool storeG = !kDupire || a.store_g != 0;
 
     // ---- stage tables
     for (int i = tid; i < table_a_size<MDL>(D, m); i += kBlock) sm.tabA[i] = a.tabA[i];
     for (int i = tid; i < table_b_size<MDL>(D, m); i += kBlock) sm.tabB[i] = a.tabB[i];
-    if (MDL == CF_MODEL_DUPIRE)
+    if (kDupire) {
         for (int i = tid; i + 1 < m; i += kBlock) sm.invdx[i] = 1.0 / (a.tabB[i + 1] - a.tabB[i]);
+        for (int i = tid; i < a.lut_n; i += kBlock) sm.lut[i] = a.lut[i];
+    }
+    for (int i = tid; i <= D; i += kBlock) sm.isev[i] = a.is_event[i];
     if (AAD) for (int i = tid; i < nAdj; i += kBlock) sm.adj[i] = 0.0;
     if (kSobol) sobol_load_low(sm.dirlow, a.sobol_dir, a.dim);
-    int p2 = 1;
-    while (p2 * 2 <= m) p2 *= 2;
+    Locator loc;
+    loc.x = sm.tabB; loc.lut = sm.lut; loc.m = m; loc.lutN = a.lut_n; loc.x0 = a.lut_x0; loc.scale = a.lut_scale;
+    loc.p2 = 1;
+    while (loc.p2 * 2 <= m) loc.p2 *= 2;
     __syncthreads();
 
     const size_t nSlots = size_t(gridDim.x) * kBlock;
     const size_t slot = size_t(blockIdx.x) * kBlock + tid;
     double* histL = a.hist;                         // Dupire: L_i            BS: S_{i+1}
-    double* histG = a.hist + size_t(D) * nSlots;    // g_i
+    double* histG = a.hist + size_t(D) * nSlots;    // g_i (when stored)
+
+    GaussGen<RNGK> gen;
+    gen.gq = sm.gq + size_t(warp) * kChunk * 32;
+    gen.tagq = sm.tagq + size_t(warp) * kChunk * 32;
+    gen.dirlow = sm.dirlow; gen.base = sm.base; gen.dim = a.dim;
 
     double paySum[kMaxPay] = {0.0, 0.0};
     double aggSum = 0.0, spotBar = 0.0;
-    const double logS0 = (MDL == CF_MODEL_DUPIRE) ? log(a.spot) : 0.0;
+    const double logS0 = kDupire ? log(a.spot) : 0.0;
 
     for (int batch = blockIdx.x; batch < a.n_batches; batch += gridDim.x) {
         const uint64_t p = uint64_t(batch) * kBlock + tid;     // path within this run
@@ -271,52 +413,58 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
         const uint64_t pabs = a.first_path + p;
 
         // ---- RNG positioning
-        SobolThread sob;
-        MrgThread mrg;
-        double sign = 1.0;
+        gen.sign = 1.0;
         if (kSobol) {
             const uint32_t n0 = uint32_t(a.first_path + uint64_t(batch) * kBlock + 1);
             const uint32_t H0 = n0 >> kLowBits;
             __syncthreads();                               // previous batch done with base[]
             sobol_block_base(sm.base, a.sobol_dir, a.dim, H0);
             __syncthreads();
-            sob.init(uint32_t(pabs + 1), H0);
+            gen.sob.init(uint32_t(pabs + 1), H0);
         } else {
-            mrg.init(a.seed1, a.seed2, pabs >> 1, a.mrg_jump);
-            sign = (pabs & 1ull) ? -1.0 : 1.0;
+            gen.mrg.init(a.seed1, a.seed2, pabs >> 1, a.mrg_jump);
+            gen.sign = (pabs & 1ull) ? -1.0 : 1.0;
         }
-        auto gauss = [&](int d) -> double {
-            if (kSobol) return inv_normal_cdf(CF_ONEOVER2POW32 * double(sob.state(sm.dirlow, sm.base, a.dim, d)));
-            return sign * inv_normal_cdf(mrg_uniform(mrg.next()));
-        };
-        auto sampleAt = [&](int e, double spotNow) -> Sample {
-            Sample s;
-            s.fwd = a.fwd_factors ? spotNow * __ldg(a.fwd_factors + e) : spotNow;
-            s.num = a.numeraires ? __ldg(a.numeraires + e) : 1.0;
-            s.disc = a.discounts ? __ldg(a.discounts + e) : 1.0;
-            return s;
+        auto bsSample = [&](int e, double spotNow) -> FwdSrc {
+            return FwdSrc(a.fwd_factors ? spotNow * __ldg(a.fwd_factors + e) : spotNow,
+                          a.numeraires ? __ldg(a.numeraires + e) : 1.0,
+                          a.discounts ? __ldg(a.discounts + e) : 1.0);
         };
 
         // ---- forward: generatePath + payoffs
         Product<PRD> prd;
         prd.init(a);
         int e = 0;
-        double X = (MDL == CF_MODEL_DUPIRE) ? logS0 : a.spot;   // Dupire: log spot, BS: spot
-        if (a.is_event[0]) {
-            prd.observe(e, E, sampleAt(e, (MDL == CF_MODEL_DUPIRE) ? exp(X) : X));
+        double X = kDupire ? logS0 : a.spot;                   // Dupire: log spot, BS: spot
+        if (sm.isev[0]) {
+            if (kDupire) { LogSpotSrc s(X); prd.observe(e, E, s); }
+            else { FwdSrc s = bsSample(e, X); prd.observe(e, E, s); }
             ++e;
         }
-        for (int i = 0; i < D; ++i) {
-            const double g = gauss(i);
-            if (MDL == CF_MODEL_DUPIRE) {
-                if (AAD) { histL[size_t(i) * nSlots + slot] = X; histG[size_t(i) * nSlots + slot] = g; }
-                const Interp it = interp_row(sm.tabB, sm.invdx, sm.tabA + i * m, m, p2, X);
-                X += it.v * (-0.5 * it.v + g);                 // mcMdlDupire.h:271
-                if (a.is_event[i + 1]) { prd.observe(e, E, sampleAt(e, exp(X))); ++e; }
-            } else {
-                X = X * exp(sm.tabA[i] + sm.tabB[i] * g);       // mcMdlBS.h:343
-                if (AAD) { histL[size_t(i) * nSlots + slot] = X; histG[size_t(i) * nSlots + slot] = g; }
-                prd.observe(e, E, sampleAt(e, X)); ++e;         // every BS step ends on an event date
+        for (int i0 = 0; i0 < D; i0 += kChunk) {
+            const int cnt = min(kChunk, D - i0);
+            gen.fill(i0, cnt);
+            for (int k = 0; k < cnt; ++k) {
+                const int i = i0 + k;
+                const double g = gen.get(k);
+                if (kDupire) {
+                    if (AAD) {
+                        histL[size_t(i) * nSlots + slot] = X;
+                        if (storeG) histG[size_t(i) * nSlots + slot] = g;
+                    }
+                    const Bucket b = loc.locate(X);
+                    const double* y = sm.tabA + i * m;
+                    double v;
+                    if (b.side != 0) v = y[b.side > 0 ? m - 1 : 0];
+                    else { const double y1 = y[b.n]; v = y1 + (y[b.n + 1] - y1) * ((X - sm.tabB[b.n]) * sm.invdx[b.n]); }
+                    X += v * (-0.5 * v + g);                   // mcMdlDupire.h:271
+                    if (sm.isev[i + 1]) { LogSpotSrc s(X); prd.observe(e, E, s); ++e; }
+                } else {
+                    X = X * exp(sm.tabA[i] + sm.tabB[i] * g);  // mcMdlBS.h:343
+                    if (AAD) { histL[size_t(i) * nSlots + slot] = X; histG[size_t(i) * nSlots + slot] = g; }
+                    FwdSrc s = bsSample(e, X);
+                    prd.observe(e, E, s); ++e;                 // every BS step ends on an event date
+                }
             }
         }
         double pay[kMaxPay] = {0.0, 0.0};
@@ -335,27 +483,39 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
 
         // ---- reverse sweep (block-synchronous: one barrier per step)
         if (AAD) {
+            __syncthreads();            // warp rows alias the Gaussian staging area of the forward sweep
             prd.begin_reverse(a.w);
             double Xbar = 0.0;          // adjoint of X_{i+1} (Dupire: log spot; BS: spot)
             int er = E - 1;
             int buf = 0;
             for (int i = D - 1; i >= 0; --i, buf ^= 1) {
                 double2* myRow = sm.wrow + size_t(buf * kWarps + warp) * rowLen;
-                const double g = histG[size_t(i) * nSlots + slot];
-                if (MDL == CF_MODEL_DUPIRE) {
-                    if (a.is_event[i + 1]) {
-                        const double S = exp(X);
-                        const SampleAdj sa = prd.reverse(er, E, sampleAt(er, S));
-                        const double ff = a.fwd_factors ? __ldg(a.fwd_factors + er) : 1.0;
-                        Xbar += sa.fwd * ff * S;            // S = exp(L)
+                if (kDupire) {
+                    if (sm.isev[i + 1]) {
+                        LogSpotSrc s(X);
+                        const SampleAdj sa = prd.reverse(er, E, s);
+                        if (sa.fwd != 0.0) Xbar += sa.fwd * s.fwd();   // dS/dL = S
                         --er;
                     }
                     const double L = histL[size_t(i) * nSlots + slot];
-                    const Interp it = interp_row(sm.tabB, sm.invdx, sm.tabA + i * m, m, p2, L);
-                    const double vbar = valid ? Xbar * (g - it.v) : 0.0;
-                    const double bb = vbar * it.t;
-                    warp_keyed_accumulate(myRow, rowLen, it.n, vbar - bb, bb);
-                    Xbar += vbar * it.slope;
+                    const Bucket b = loc.locate(L);
+                    const double* y = sm.tabA + i * m;
+                    double v, t, slope;
+                    if (b.side != 0) {
+                        const bool right = b.side > 0;
+                        v = y[right ? m - 1 : 0]; t = (right && m > 1) ? 1.0 : 0.0; slope = 0.0;
+                    } else {
+                        const double y1 = y[b.n], dy = y[b.n + 1] - y1, idx = sm.invdx[b.n];
+                        t = (L - sm.tabB[b.n]) * idx;
+                        v = y1 + dy * t;
+                        slope = dy * idx;
+                    }
+                    // g_i - v_i: stored, or recovered from L_{i+1} = L_i + v (g - v/2)
+                    const double gmv = storeG ? histG[size_t(i) * nSlots + slot] - v : (X - L) / v - 0.5 * v;
+                    const double vbar = valid ? Xbar * gmv : 0.0;
+                    const double bb = vbar * t;
+                    warp_keyed_accumulate(myRow, rowLen, b.n, vbar - bb, bb);
+                    Xbar += vbar * slope;
                     X = L;
                     __syncthreads();
                     if (tid < m) {
@@ -369,8 +529,9 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
                     }
                 } else {
                     // BS: X currently holds S_{i+1}
+                    const double g = histG[size_t(i) * nSlots + slot];
                     const double S1 = X;
-                    const Sample smp = sampleAt(er, S1);
+                    FwdSrc smp = bsSample(er, S1);
                     const SampleAdj sa = prd.reverse(er, E, smp);
                     const double ff = a.fwd_factors ? __ldg(a.fwd_factors + er) : 1.0;
                     Xbar += sa.fwd * ff;
@@ -398,14 +559,17 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
                 }
             }
             // today's sample (timeline point 0)
-            if (a.is_event[0]) {
-                const double S = (MDL == CF_MODEL_DUPIRE) ? exp(X) : X;
-                const Sample smp = sampleAt(0, S);
-                const SampleAdj sa = prd.reverse(0, E, smp);
-                const double ff = a.fwd_factors ? __ldg(a.fwd_factors) : 1.0;
-                Xbar += (MDL == CF_MODEL_DUPIRE) ? sa.fwd * ff * S : sa.fwd * ff;
-                if (MDL == CF_MODEL_BS) {
-                    double v2 = warp_sum(valid ? sa.num : 0.0), v3 = warp_sum(valid ? sa.fwd * S : 0.0);
+            if (sm.isev[0]) {
+                if (kDupire) {
+                    LogSpotSrc s(X);
+                    const SampleAdj sa = prd.reverse(0, E, s);
+                    if (sa.fwd != 0.0) Xbar += sa.fwd * s.fwd();
+                } else {
+                    FwdSrc smp = bsSample(0, X);
+                    const SampleAdj sa = prd.reverse(0, E, smp);
+                    const double ff = a.fwd_factors ? __ldg(a.fwd_factors) : 1.0;
+                    Xbar += sa.fwd * ff;
+                    double v2 = warp_sum(valid ? sa.num : 0.0), v3 = warp_sum(valid ? sa.fwd * X : 0.0);
                     double v4 = warp_sum(valid ? sa.disc : 0.0);
                     __syncthreads();
                     if (lane == 0) { sm.wrow[warp * rowLen] = make_double2(v2, v3); sm.wrow[warp * rowLen + 1] = make_double2(v4, 0.0); }
@@ -422,7 +586,7 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
             }
             __syncthreads();
             // spot leaf: Dupire L0 = log(S0) -> 1/S0 (mcMdlDupire.h:245); BS: S_0 = spot
-            if (valid) spotBar += (MDL == CF_MODEL_DUPIRE) ? Xbar / a.spot : Xbar;
+            if (valid) spotBar += kDupire ? Xbar / a.spot : Xbar;
         }
     }
 

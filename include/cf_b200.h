@@ -176,6 +176,15 @@ int cf_rng_draw(const cf_rng* rng, int dim, uint64_t first_path, uint64_t n_path
 int cf_mrg_numerators(const cf_rng* rng, int dim, uint64_t first_path, uint64_t n_paths, uint32_t* out);
 int cf_inv_normal(const double* p, double* out, uint64_t n);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py): scalar FP64 DFMA peak of the bound device in TFLOP/s
+ * (2 flops per DFMA, 8 independent chains per thread, best of 4 timed launches) -- the roofline
+ * denominator of this FP64-pipe-bound path; and the SM count.
+ * ---------------------------------------------------------------------------------------- */
+int cf_measure_fp64_peak(double* tflops, double* ms);
+int cf_device_sm_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,32 @@
+"""Run the config-3 (Dupire x UOC, 156 steps, 30x36 surface) AAD kernel a few times: target for ncu."""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from compfinance_b200 import capi
+from oracle import restate as R
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+mode = sys.argv[3] if len(sys.argv) > 3 else "aad"
+eng = capi.Engine(device=0)
+spots = np.arange(55, 201, 5.0); times = np.arange(1, 37) / 12.0
+vols = 0.15 + 0.10 * np.log(spots[:, None] / 100) ** 2 + 0.02 * times[None, :]
+ptl = R.uoc_timeline(3.0, 1.0 / 52)
+tab = R.DupireTables(100, spots, times, vols, 0.25, ptl)
+mdl = eng.dupire_model(100.0, tab.log_spots, tab.interp_vols, tab.common, len(ptl))
+prd = eng.uoc(120.0, 150.0, float(np.exp(np.log(100.0)) * 0.01), len(ptl))
+rg = eng.rng("sobol")
+plan = C.c_void_p()
+eng._chk(eng.lib.cf_plan_create(C.byref(mdl), C.byref(prd), C.byref(rg), C.byref(plan)))
+dout = torch.zeros(eng.lib.cf_plan_out_size(plan, 1), dtype=torch.float64, device="cuda")
+wv = (C.c_double * 2)(1.0, 0.0)
+for it in range(iters):
+    if mode == "aad":
+        eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, 0, N, dout.data_ptr(), None))
+    else:
+        eng._chk(eng.lib.cf_plan_launch_value(plan, 0, N, dout.data_ptr(), None))
+torch.cuda.synchronize()
+ms = C.c_double(); nl = C.c_int()
+eng._chk(eng.lib.cf_plan_kernel_ms(plan, C.byref(ms), C.byref(nl)))
+print(mode, "kernel avg ms", ms.value, "paths/s %.4g" % (N / ms.value * 1e3), "fp64 peak TF", eng.fp64_peak_tflops())

@@ -33,6 +33,7 @@ class cf_model(C.Structure):
         ("bs_drifts", _dp), ("bs_stds", _dp),
         ("numeraires", _dp), ("fwd_factors", _dp), ("discounts", _dp),
         ("n_knots", C.c_int32), ("log_spots", _dp), ("interp_vols", _dp),
+        ("n_times", C.c_int32), ("time_col1", _ip), ("time_col2", _ip), ("time_w1", _dp), ("time_w2", _dp),
         ("dlm_spots", _dp), ("dlm_chol", _dp), ("dlm_alphas", _dp), ("dlm_dynamics", _ip),
         ("dlm_dyn_fwd", _dp), ("dlm_drifts", _dp), ("dlm_stds", _dp), ("dlm_fwd_factors", _dp),
     ]
@@ -110,7 +111,8 @@ class Engine:
     def rng(self, kind, seed1=12345, seed2=12346):
         return cf_rng(CF_RNG_SOBOL if kind == "sobol" else CF_RNG_MRG32K3A, seed1, seed2)
 
-    def dupire_model(self, spot, log_spots, interp_vols, is_event, n_events):
+    def dupire_model(self, spot, log_spots, interp_vols, is_event, n_events, time_map=None):
+        """time_map = (n_times, col1[D], col2[D], w1[D], w2[D]) folds Dupire::init() into the device sweep."""
         keep = []
         ls, pls = self._d(log_spots); keep.append(ls)
         iv, piv = self._d(interp_vols); keep.append(iv)
@@ -119,6 +121,13 @@ class Engine:
         m.kind, m.n_assets, m.n_steps, m.n_events = CF_MODEL_DUPIRE, 1, iv.shape[0], n_events
         m.is_event = ev.ctypes.data_as(_u8p)
         m.spot, m.n_knots, m.log_spots, m.interp_vols = spot, ls.size, pls, piv
+        if time_map is not None:
+            nt, c1, c2, w1, w2 = time_map
+            c1 = np.ascontiguousarray(c1, dtype=np.int32); c2 = np.ascontiguousarray(c2, dtype=np.int32)
+            w1, pw1 = self._d(w1); w2, pw2 = self._d(w2)
+            keep += [c1, c2, w1, w2]
+            m.n_times, m.time_col1, m.time_col2 = nt, c1.ctypes.data_as(_ip), c2.ctypes.data_as(_ip)
+            m.time_w1, m.time_w2 = pw1, pw2
         m._keep = keep
         return m
 

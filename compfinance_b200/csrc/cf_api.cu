@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "cf_dupire.cuh"
 #include "cf_kernels.cuh"
 #include "cf_tables.h"
 
@@ -104,7 +105,11 @@ size_t smem_for(int mdl, bool aad, int D, int m, int E, int dim, bool sobol, int
 
 size_t adj_size(const cf_model* mdl)
 {
-    if (mdl->kind == CF_MODEL_DUPIRE) return 1 + size_t(mdl->n_steps) * mdl->n_knots;
+    if (mdl->kind == CF_MODEL_DUPIRE) {
+        if (mdl->n_times > 0 && mdl->time_col1 && mdl->time_col2 && mdl->time_w1 && mdl->time_w2)
+            return 1 + size_t(mdl->n_knots) * mdl->n_times;
+        return 1 + size_t(mdl->n_steps) * mdl->n_knots;
+    }
     if (mdl->kind == CF_MODEL_BS) return 1 + 2 * size_t(mdl->n_steps) + 3 * size_t(mdl->n_events);
     throw CfError("cf_b200: model kind not implemented");
 }
@@ -150,6 +155,13 @@ struct cf_plan {
     DevBuf<uint64_t> mrgJump;
     DevBuf<uint8_t> lut;
     int lutN = 0, storeG = 1;
+    // Dupire fast kernel (cf_dupire.cuh)
+    bool fast = false, hasTimeMap = false;
+    int nTimes = 0;
+    DevBuf<int32_t> tk1, tk2;
+    DevBuf<double> tc1, tc2, wtab, scratch;
+    int wtabGrid = 0;
+    cf::DArgs dbase{};
     DevBuf<double> hist, partial;
     int histGrid = 0, partialGrid = 0, partialStride = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // recorded since last query
@@ -163,6 +175,14 @@ struct cf_plan {
 
     size_t outSize(bool aad) const { return aad ? size_t(nPay) + 1 + nAdj : size_t(nPay); }
 
+    std::pair<cudaEvent_t, cudaEvent_t> takeEvents()
+    {
+        std::pair<cudaEvent_t, cudaEvent_t> ev;
+        if (!pool.empty()) { ev = pool.back(); pool.pop_back(); }
+        else { CF_CUDA(cudaEventCreate(&ev.first)); CF_CUDA(cudaEventCreate(&ev.second)); }
+        return ev;
+    }
+
     void launch(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut, double* dPerPath,
                 double* dPerAgg, cudaStream_t s)
     {
@@ -171,14 +191,17 @@ struct cf_plan {
         const uint64_t nb64 = (n + cf::kBlock - 1) / cf::kBlock;
         if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
         const int nBatches = int(nb64);
+        if (fast && (!aad || hasTimeMap)) { launchFast(aad, w, first, n, nBatches, dOut, dPerPath, dPerAgg, s); return; }
+
         const int grid = std::min(nBatches, 2 * g_sms);
-        const size_t stride = outSize(aad) + (aad ? 0 : 0);
+        const size_t tabAdj = mdlKind == CF_MODEL_DUPIRE ? 1 + size_t(D) * m : nAdj;   // generic kernel: table adjoints
+        const size_t stride = aad ? size_t(nPay) + 1 + tabAdj : size_t(nPay);
         if (partialGrid < grid || partialStride < int(stride)) {
             partial.alloc(size_t(grid) * stride);
             partialGrid = grid; partialStride = int(stride);
         }
         if (aad && histGrid < grid) {
-            hist.alloc(size_t(storeG ? 2 : 1) * D * size_t(grid) * cf::kBlock);
+            hist.alloc(size_t(2) * D * size_t(grid) * cf::kBlock);
             histGrid = grid;
         }
         cf::KArgs a = base;
@@ -192,16 +215,68 @@ struct cf_plan {
         const size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL, lutN);
         if (smem > 227 * 1024) throw CfError("cf_b200: tables do not fit in shared memory (n_steps * n_knots too large)");
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        std::pair<cudaEvent_t, cudaEvent_t> ev;
-        if (!pool.empty()) { ev = pool.back(); pool.pop_back(); }
-        else { CF_CUDA(cudaEventCreate(&ev.first)); CF_CUDA(cudaEventCreate(&ev.second)); }
+        auto ev = takeEvents();
+        CF_CUDA(cudaEventRecord(ev.first, s));
+        fn<<<grid, cf::kBlock, smem, s>>>(a);
+        CF_CUDA(cudaEventRecord(ev.second, s));
+        events.push_back(ev);
+        CF_CUDA(cudaGetLastError());
+        if (aad && mdlKind == CF_MODEL_DUPIRE && hasTimeMap) {
+            // generic kernel produced interp_vols adjoints: reduce, then apply the time map
+            if (scratch.n < stride) scratch.alloc(stride);
+            cf::reduce_partials_kernel<<<(int(stride) + 127) / 128, 128, 0, s>>>(partial.p, grid, partialStride, int(stride), scratch.p);
+            const int nOut = int(outSize(true));
+            cf::collapse_time_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(scratch.p, nPay + 2, D, m, nTimes, tk1.p, tk2.p, tc1.p, tc2.p, dOut);
+            g_launches += 1;
+        } else {
+            const int nOut = int(outSize(aad));
+            cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(partial.p, grid, partialStride, nOut, dOut);
+        }
+        CF_CUDA(cudaGetLastError());
+        g_launches += 2;
+    }
+
+    template <int PRD>
+    static void (*pickFast(bool aad, int rng))(const cf::DArgs)
+    {
+        if (aad) return rng == CF_RNG_SOBOL ? cf::dupire_kernel<PRD, true, CF_RNG_SOBOL> : cf::dupire_kernel<PRD, true, CF_RNG_MRG32K3A>;
+        return rng == CF_RNG_SOBOL ? cf::dupire_kernel<PRD, false, CF_RNG_SOBOL> : cf::dupire_kernel<PRD, false, CF_RNG_MRG32K3A>;
+    }
+
+    void launchFast(bool aad, const double* w, uint64_t first, uint64_t n, int nBatches, double* dOut,
+                    double* dPerPath, double* dPerAgg, cudaStream_t s)
+    {
+        const int grid = std::min(nBatches, 3 * g_sms);
+        const size_t stride = size_t(nPay) + 2;
+        if (partialGrid < grid || partialStride < int(stride)) {
+            partial.alloc(size_t(grid) * stride);
+            partialGrid = grid; partialStride = int(stride);
+        }
+        if (aad && histGrid < grid) {
+            hist.alloc(size_t(storeG ? 2 : 1) * D * size_t(grid) * cf::kBlock);
+            histGrid = grid;
+        }
+        if (aad && wtabGrid < grid) {
+            wtab.alloc(size_t(grid) * cf::kWarps * size_t(nTimes) * m);
+            wtabGrid = grid;
+        }
+        cf::DArgs a = dbase;
+        a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
+        a.w[0] = a.w[1] = 0.0;
+        if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
+        a.partial = partial.p; a.wtab = wtab.p; a.hist = hist.p;
+        a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg;
+        auto fn = prdKind == CF_PRODUCT_UOC ? pickFast<CF_PRODUCT_UOC>(aad, rngKind) : pickFast<CF_PRODUCT_EUROPEAN>(aad, rngKind);
+        const size_t smem = cf::dupire_smem(D, m, dim, rngKind == CF_RNG_SOBOL, lutN, aad).total;
+        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        auto ev = takeEvents();
         CF_CUDA(cudaEventRecord(ev.first, s));
         fn<<<grid, cf::kBlock, smem, s>>>(a);
         CF_CUDA(cudaEventRecord(ev.second, s));
         events.push_back(ev);
         CF_CUDA(cudaGetLastError());
         const int nOut = int(outSize(aad));
-        cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(partial.p, grid, partialStride, nOut, dOut);
+        cf::dupire_reduce_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(partial.p, grid, nPay, wtab.p, grid * cf::kWarps, m, nTimes, aad ? 1 : 0, dOut);
         CF_CUDA(cudaGetLastError());
         g_launches += 2;
     }
@@ -276,6 +351,32 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     a.tabA = p->tabA.p; a.tabB = p->tabB.p;
     a.numeraires = p->num.p; a.fwd_factors = p->ff.p; a.discounts = p->disc.p;
     a.lut = p->lut.p; a.lut_n = p->lutN; a.store_g = p->storeG;
+    if (mdl->kind == CF_MODEL_DUPIRE) {
+        p->hasTimeMap = mdl->n_times > 0 && mdl->time_col1 && mdl->time_col2 && mdl->time_w1 && mdl->time_w2;
+        if (p->hasTimeMap) {
+            p->nTimes = mdl->n_times;
+            for (int i = 0; i < p->D; ++i)
+                if (mdl->time_col1[i] < 0 || mdl->time_col1[i] >= p->nTimes || mdl->time_col2[i] < 0 || mdl->time_col2[i] >= p->nTimes)
+                    throw CfError("cf_b200: Dupire time map column out of range");
+            p->tk1.upload(mdl->time_col1, size_t(p->D)); p->tk2.upload(mdl->time_col2, size_t(p->D));
+            p->tc1.upload(mdl->time_w1, size_t(p->D)); p->tc2.upload(mdl->time_w2, size_t(p->D));
+            CF_CUDA(cudaStreamSynchronize(nullptr));
+        }
+        // the warp-independent kernel needs the bucket LUT, 2..32 knots and a timeline that ends on an event date
+        p->fast = p->lutN > 0 && p->m >= 2 && p->m <= 32 && mdl->is_event[p->D] != 0
+                  && cf::dupire_smem(p->D, p->m, p->dim, rng->kind == CF_RNG_SOBOL, p->lutN, true).total <= 75 * 1024;
+        cf::DArgs& d = p->dbase;
+        d.seed1 = rng->seed1; d.seed2 = rng->seed2; d.dim = p->dim;
+        d.sobol_dir = p->sobolDir.p; d.mrg_jump = p->mrgJump.p;
+        d.n_steps = p->D; d.n_events = p->E; d.n_knots = p->m; d.n_times = p->nTimes;
+        d.is_event = p->isEvent.p; d.spot = mdl->spot;
+        d.interp_vols = p->tabA.p; d.log_spots = p->tabB.p;
+        d.lut = p->lut.p; d.lut_n = p->lutN; d.lut_x0 = p->base.lut_x0; d.lut_scale = p->base.lut_scale;
+        d.store_g = p->storeG;
+        d.k1 = p->tk1.p; d.k2 = p->tk2.p; d.c1 = p->tc1.p; d.c2 = p->tc2.p;
+        d.n_payoffs = prd->n_payoffs; d.is_put = prd->is_put;
+        d.strike = prd->strike; d.barrier = prd->barrier; d.smooth = prd->smooth;
+    }
     a.n_payoffs = prd->n_payoffs; a.is_put = prd->is_put;
     a.strike = prd->strike; a.barrier = prd->barrier; a.smooth = prd->smooth;
     return p;

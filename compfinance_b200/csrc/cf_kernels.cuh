@@ -617,4 +617,26 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
     out[k] = s;
 }
 
+
+// in: [nHead] head values then ybar[D][m] (adjoints of interp_vols).  out: head then volsbar[m][nTimes]
+// with volsbar[j][k] = sum_i (k1[i] == k ? c1[i] : 0) * ybar[i][j] + (k2[i] == k ? c2[i] : 0) * ybar[i][j]
+__global__ void collapse_time_kernel(const double* __restrict__ in, int nHead, int D, int m, int nTimes,
+                                     const int32_t* __restrict__ k1, const int32_t* __restrict__ k2,
+                                     const double* __restrict__ c1, const double* __restrict__ c2,
+                                     double* __restrict__ out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nHead) { out[q] = in[q]; return; }
+    const int r = q - nHead;
+    if (r >= m * nTimes) return;
+    const int j = r / nTimes, k = r % nTimes;
+    double s = 0.0;
+    for (int i = D - 1; i >= 0; --i) {
+        const double y = in[nHead + i * m + j];
+        if (k1[i] == k) s += c1[i] * y;
+        if (k2[i] == k) s += c2[i] * y;
+    }
+    out[q] = s;
+}
+
 }  // namespace cf

@@ -67,6 +67,16 @@ typedef struct cf_model {
     int32_t       n_knots;         /* spot knots of the local-vol surface */
     const double* log_spots;       /* [n_knots] */
     const double* interp_vols;     /* [n_steps][n_knots]  sqrt(dt_i) * vol(spot_j, t_i) */
+    /* Optional: Dupire::init() as a linear map (mcMdlDupire.h:202-216: time interpolation x sqrt(dt))
+     *   interp_vols[i][j] = time_w1[i] * vols[j][time_col1[i]] + time_w2[i] * vols[j][time_col2[i]]
+     * When all four arrays are given (n_times > 0) cf_run_aad folds this map into the accumulation and
+     * returns the adjoints of vols ([n_knots][n_times], the parameter order of mcMdlDupire.h:116-121)
+     * instead of the adjoints of interp_vols.  The host mirror derives the map from its own tape of init(). */
+    int32_t        n_times;
+    const int32_t* time_col1;      /* [n_steps] */
+    const int32_t* time_col2;      /* [n_steps] (may equal time_col1 with weight 0) */
+    const double*  time_w1;        /* [n_steps] */
+    const double*  time_w2;        /* [n_steps] */
 
     /* Multi-asset displaced model tables, mcMdlMultiDisplaced.h:474-606 */
     const double*  dlm_spots;      /* [n_assets] */
@@ -118,7 +128,8 @@ uint64_t cf_launch_count(void);
 
 /* Number of doubles in the table-adjoint vector of (model, product):
  *   BS      : 1 (spot) + n_steps (drifts) + n_steps (stds) + 3 * n_events (numeraire, fwd factor, discount)
- *   Dupire  : 1 (spot) + n_steps * n_knots (interp_vols, step-major)
+ *   Dupire  : 1 (spot) + n_steps * n_knots (interp_vols, step-major), or, when the time map is
+ *             given, 1 (spot) + n_knots * n_times (vols, spot-major)
  *   Displaced: see cf_b200.h of later rounds (not implemented yet). */
 size_t cf_table_adjoint_size(const cf_model* mdl, const cf_product* prd);
 

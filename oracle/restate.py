@@ -288,6 +288,19 @@ class DupireTables:
             for j in range(len(self.spots)):
                 self.interp_vols[i, j] = self.sqrt_dt[i] * interp1(self.times, list(self.vols[j]), self.timeline[i])
 
+    def time_map(self):
+        """init() (mcMdlDupire.h:202-216) as a linear map per step: interp_vols[i][j] =
+        w1[i] * vols[j][col1[i]] + w2[i] * vols[j][col2[i]].  Returns (n_times, col1, col2, w1, w2)."""
+        c1, c2, w1, w2 = [], [], [], []
+        for i in range(self.n_steps):
+            ws = interp1_weights(self.times, self.timeline[i])
+            c1.append(ws[0][0]); w1.append(self.sqrt_dt[i] * ws[0][1])
+            if len(ws) > 1:
+                c2.append(ws[1][0]); w2.append(self.sqrt_dt[i] * ws[1][1])
+            else:
+                c2.append(ws[0][0]); w2.append(0.0)
+        return len(self.times), np.array(c1, dtype=np.int32), np.array(c2, dtype=np.int32), np.array(w1), np.array(w2)
+
     def param_risks(self, spot_adj, ybar, n_paths):
         """propagateMarkToStart for init() (mcMdlDupire.h:202-216): interp_vols adjoints -> vols
         adjoints; then risks = adjoint / nPath (mcBase.h:745)."""

@@ -31,6 +31,7 @@ vols = 0.15 + 0.10 * np.log(spots[:, None] / 100) ** 2 + 0.02 * times[None, :]
 ptl = R.uoc_timeline(3.0, 1.0 / 52)
 tab = R.DupireTables(100, spots, times, vols, 0.25, ptl)
 mdl = eng.dupire_model(100.0, tab.log_spots, tab.interp_vols, tab.common, len(ptl))
+mdlT = eng.dupire_model(100.0, tab.log_spots, tab.interp_vols, tab.common, len(ptl), time_map=tab.time_map())
 smooth_abs = float(np.exp(np.log(100.0)) * 0.01)
 prd = eng.uoc(120.0, 150.0, smooth_abs, len(ptl))
 w = [0.7, 0.3]
@@ -46,8 +47,14 @@ for rngname, rt in [("sobol", ("sobol",)), ("mrg", ("mrg32k3a", 12345, 12346))]:
               f"aad per-path {np.abs(r['payoffs'] - o['payoffs']).max():.3e} agg {np.abs(r['agg'] - o['agg']).max():.3e}",
               f"spot_adj rel {abs(r['table_adj'][0] / o['spot_adj'] - 1):.3e}",
               f"ybar max abs {np.abs(r['table_adj'][1:].reshape(tab.n_steps, -1) - o['ybar']).max():.3e} (scale {np.abs(o['ybar']).max():.3e})", f"t={dt:.2f}s")
+        rT = eng.run_aad(mdlT, prd, eng.rng(rngname), first, N, w, per_path=True)
+        so, vo = tab.param_risks(o['spot_adj'], o['ybar'], N)
+        vT = rT['table_adj'][1:].reshape(len(spots), len(times)) / N
+        big = np.abs(vo) > 1e-6
+        print(f"   fast kernel: per-path {np.abs(rT['payoffs'] - o['payoffs']).max():.3e} agg {np.abs(rT['agg'] - o['agg']).max():.3e}",
+              f"delta rel {abs(rT['table_adj'][0] / N / so - 1):.3e} vega max abs {np.abs(vT - vo).max():.3e} max rel(>1e-6) {np.abs(vT[big] / vo[big] - 1).max():.3e}")
 # determinism
-r1 = eng.run_aad(mdl, prd, eng.rng("sobol"), 0, 1 << 15, w); r2 = eng.run_aad(mdl, prd, eng.rng("sobol"), 0, 1 << 15, w)
+r1 = eng.run_aad(mdlT, prd, eng.rng("sobol"), 0, 1 << 15, w); r2 = eng.run_aad(mdlT, prd, eng.rng("sobol"), 0, 1 << 15, w)
 print("bitwise deterministic:", bool((r1["table_adj"] == r2["table_adj"]).all() and r1["agg_sum"] == r2["agg_sum"]))
 
 # BS x European / UOC
@@ -71,14 +78,14 @@ for rngname, rt in [("sobol", ("sobol",)), ("mrg", ("mrg32k3a", 12345, 12346))]:
 # quick timing config 3
 import ctypes as C
 N = 1 << 20
-t = time.time(); r = eng.run_aad(mdl, prd, eng.rng("sobol"), 0, N, [1.0, 0.0]); print("config3 AAD one-shot wall", time.time() - t)
-t = time.time(); r = eng.run_aad(mdl, prd, eng.rng("sobol"), 0, N, [1.0, 0.0]); print("config3 AAD one-shot wall (2nd)", time.time() - t)
-sr, vr = tab.param_risks(r["table_adj"][0], r["table_adj"][1:].reshape(tab.n_steps, -1), N)
+t = time.time(); r = eng.run_aad(mdlT, prd, eng.rng("sobol"), 0, N, [1.0, 0.0]); print("config3 AAD one-shot wall", time.time() - t)
+t = time.time(); r = eng.run_aad(mdlT, prd, eng.rng("sobol"), 0, N, [1.0, 0.0]); print("config3 AAD one-shot wall (2nd)", time.time() - t)
+sr, vr = r["table_adj"][0] / N, r["table_adj"][1:].reshape(len(spots), len(times)) / N
 print("value %.17g delta %.17g sumvega %.17g vega[13][11] %.17g" % (r["agg_sum"] / N, sr, vr.sum(), vr[13][11]))
 print("ref:  0.96926107424976005 0.020804057371458962 -5.4262407757753115 -0.024065608611340886")
 plan = C.c_void_p()
 rg = eng.rng("sobol")
-eng._chk(eng.lib.cf_plan_create(C.byref(mdl), C.byref(prd), C.byref(rg), C.byref(plan)))
+eng._chk(eng.lib.cf_plan_create(C.byref(mdlT), C.byref(prd), C.byref(rg), C.byref(plan)))
 import torch
 nout = eng.lib.cf_plan_out_size(plan, 1)
 dout = torch.zeros(nout, dtype=torch.float64, device="cuda")

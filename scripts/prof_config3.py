@@ -14,7 +14,7 @@ spots = np.arange(55, 201, 5.0); times = np.arange(1, 37) / 12.0
 vols = 0.15 + 0.10 * np.log(spots[:, None] / 100) ** 2 + 0.02 * times[None, :]
 ptl = R.uoc_timeline(3.0, 1.0 / 52)
 tab = R.DupireTables(100, spots, times, vols, 0.25, ptl)
-mdl = eng.dupire_model(100.0, tab.log_spots, tab.interp_vols, tab.common, len(ptl))
+mdl = eng.dupire_model(100.0, tab.log_spots, tab.interp_vols, tab.common, len(ptl), time_map=tab.time_map())
 prd = eng.uoc(120.0, 150.0, float(np.exp(np.log(100.0)) * 0.01), len(ptl))
 rg = eng.rng("sobol")
 plan = C.c_void_p()

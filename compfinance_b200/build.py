@@ -35,5 +35,28 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(LIB_DIR, "libcf_host.so")
+HOST_DEPS = ["cf_export.cpp", "cf_main.h", "cf_store.h", "cf_products.h", "cf_models.h", "cf_rng.h", "cf_base.h",
+             "cf_aad.h", "cf_matrix.h", "cf_util.h"]
+
+
+def build_host(force=False):
+    """Host C++17 mirror of the reference API (compfinance_b200/host) -> libcf_host.so, linked to the engine."""
+    build(force=False)
+    if not force and os.path.exists(HOST_LIB):
+        t = os.path.getmtime(HOST_LIB)
+        deps = [os.path.join(HOST_DIR, d) for d in HOST_DEPS if os.path.exists(os.path.join(HOST_DIR, d))]
+        deps += [os.path.join(HERE, "..", "include", "cf_b200.h"), LIB]
+        if all(os.path.getmtime(d) <= t for d in deps):
+            return HOST_LIB
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", os.path.join(HOST_DIR, "cf_export.cpp"),
+           "-o", HOST_LIB, "-L" + LIB_DIR, "-lcf_b200", "-Wl,-rpath,$ORIGIN"]
+    print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_host(force="--force" in sys.argv)

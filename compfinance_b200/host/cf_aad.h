@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstddef>
 #include <stdexcept>
+#include <utility>
 #include <vector>
 
 struct AADNode {
@@ -54,6 +55,20 @@ public:
     iterator begin() const { return 0; }
     iterator end() const { return myNodes.size(); }
     iterator markIt() const { return myMark; }
+
+    // d node / d leaf for every leaf under `node`, by walking its (small) expression DAG.
+    // Used to read a table entry of init() as a sparse linear map of the parameters.
+    void leafGradient(int node, double seed, std::vector<std::pair<int, double>>& out) const
+    {
+        const AADNode& n = myNodes[size_t(node)];
+        if (n.nArg == 0) {
+            for (auto& e : out) if (e.first == node) { e.second += seed; return; }
+            out.emplace_back(node, seed);
+            return;
+        }
+        for (int k = 0; k < n.nArg; ++k)
+            if (n.der[k] != 0.0) leafGradient(n.arg[k], seed * n.der[k], out);
+    }
 
     // reverse sweep over nodes [to, from], from >= to
     void propagate(iterator from, iterator to)
@@ -128,7 +143,7 @@ public:
     friend Number operator/(const Number& a, const Number& b)
     {
         const double inv = 1.0 / b.myValue;
-        return binary(a.myValue * inv, a, inv, b, -a.myValue * inv * inv);
+        return binary(a.myValue / b.myValue, a, inv, b, -a.myValue * inv * inv);
     }
     friend Number operator+(const Number& a, const double b) { return unary(a.myValue + b, a, 1.0); }
     friend Number operator+(const double a, const Number& b) { return unary(a + b.myValue, b, 1.0); }

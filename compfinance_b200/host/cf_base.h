@@ -1,0 +1,381 @@
+// cf_base.h -- host mirror of the reference's simulation abstractions (mcBase.h) with the six
+// template algorithms re-implemented on top of the CUDA engine (include/cf_b200.h).
+//
+// Kept from the reference, same names and meaning (mcBase.h:45-246): Time / systemTime, SampleDef,
+// Sample<T>, Scenario<T>, allocatePath, initializePath, Product<T>, Model<T>, RNG, and the free
+// functions mcSimul (:267), mcParallelSimul (:314), mcSimulAAD (:429), mcParallelSimulAAD (:566)
+// with their result structs.  What changes: the path loops run on the GPU.  A concrete model or
+// product takes part by describing itself to the engine through deviceImage(); the host keeps
+// everything path-independent (timelines, init() tables, the chain rule from tables to parameters
+// on a small host tape = the reference's propagateMarkToStart, mcBase.h:518 / 721-733).
+//
+// There is no CPU path: generatePath()/payoffs() of the built-in classes are not evaluated on the
+// host, and a model/product without a device image makes the algorithms throw runtime_error
+// (the reference's error convention, mcBase.h:273).
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <iomanip>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/cf_b200.h"
+#include "cf_aad.h"
+#include "cf_matrix.h"
+
+using Time = double;
+inline Time systemTime = 0.0;     // mcBase.cpp:22
+
+// ---------------------------------------------------------------------------------------------
+// Scenarios (mcBase.h:45-117)
+// ---------------------------------------------------------------------------------------------
+struct SampleDef
+{
+    bool numeraire = true;
+    struct RateDef
+    {
+        Time start, end;
+        std::string curve;
+        RateDef(const Time s, const Time e, const std::string& c) : start(s), end(e), curve(c) {}
+    };
+    std::vector<Time>               discountMats;
+    std::vector<RateDef>            liborDefs;
+    std::vector<std::vector<Time>>  forwardMats;   // forwardMats[a] = maturities for asset a
+};
+
+template <class T>
+struct Sample
+{
+    T                           numeraire;
+    std::vector<T>              discounts;
+    std::vector<T>              libors;
+    std::vector<std::vector<T>> forwards;
+
+    void allocate(const SampleDef& data)
+    {
+        discounts.resize(data.discountMats.size());
+        libors.resize(data.liborDefs.size());
+        forwards.resize(data.forwardMats.size());
+        for (size_t a = 0; a < forwards.size(); ++a) forwards[a].resize(data.forwardMats[a].size());
+    }
+    void initialize()
+    {
+        numeraire = T(1.0);
+        std::fill(discounts.begin(), discounts.end(), T(1.0));
+        std::fill(libors.begin(), libors.end(), T(0.0));
+        for (auto& f : forwards) std::fill(f.begin(), f.end(), T(100.0));
+    }
+};
+
+template <class T> using Scenario = std::vector<Sample<T>>;
+
+template <class T>
+inline void allocatePath(const std::vector<SampleDef>& defline, Scenario<T>& path)
+{
+    path.resize(defline.size());
+    for (size_t i = 0; i < defline.size(); ++i) path[i].allocate(defline[i]);
+}
+template <class T>
+inline void initializePath(Scenario<T>& path) { for (auto& s : path) s.initialize(); }
+
+// ---------------------------------------------------------------------------------------------
+// Device images: flat, self-owning descriptions handed to the C ABI
+// ---------------------------------------------------------------------------------------------
+struct ModelImage
+{
+    cf_model pod{};
+    std::vector<uint8_t> isEvent;
+    std::vector<double>  tabA, tabB, numeraires, fwdFactors, discounts;
+    std::vector<int32_t> col1, col2;
+    std::vector<double>  w1, w2;
+    // value of forwards[0][0] on the first sample when that sample is today (UOC smoothing, mcPrd.h:247)
+    bool   firstSampleIsToday = false;
+    double firstSampleForward = 0.0;
+    // AAD: for each slot of the device adjoint vector, the host-tape Number it belongs to
+    std::vector<Number*> adjointTargets;
+};
+
+struct ProductImage
+{
+    cf_product pod{};
+    std::vector<int32_t> strikeOffsets;
+    std::vector<double>  strikes, weights, eventDt;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Products, models, RNGs (mcBase.h:122-246)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+class Product
+{
+    inline static const std::vector<std::string> defaultAssetNames = {"spot"};
+
+public:
+    virtual const std::vector<Time>& timeline() const = 0;
+    virtual const std::vector<SampleDef>& defline() const = 0;
+    virtual const size_t numAssets() const { return 1; }
+    virtual const std::vector<std::string>& assetNames() const { return defaultAssetNames; }
+    virtual const std::vector<std::string>& payoffLabels() const = 0;
+
+    // Payoffs of one path.  The built-in products are evaluated on the device inside the path
+    // kernels; this host entry exists for interface compatibility and throws unless overridden.
+    virtual void payoffs(const Scenario<T>& /*path*/, std::vector<T>& /*payoffs*/) const
+    {
+        throw std::runtime_error("Product::payoffs(): paths are evaluated on the GPU, no host evaluation");
+    }
+
+    virtual std::unique_ptr<Product<T>> clone() const = 0;
+    virtual ~Product() {}
+
+    // Describe the payoff to the CUDA engine.  Return false if the product cannot run on the device.
+    virtual bool deviceImage(ProductImage& /*img*/, const ModelImage& /*mdl*/) const { return false; }
+};
+
+template <class T>
+class Model
+{
+    inline static const std::vector<std::string> defaultAssetNames = {"spot"};
+
+public:
+    virtual const size_t numAssets() const { return 1; }
+    virtual const std::vector<std::string>& assetNames() const { return defaultAssetNames; }
+
+    virtual void allocate(const std::vector<Time>& prdTimeline, const std::vector<SampleDef>& prdDefline) = 0;
+    virtual void init(const std::vector<Time>& prdTimeline, const std::vector<SampleDef>& prdDefline) = 0;
+    virtual size_t simDim() const = 0;
+
+    virtual void generatePath(const std::vector<double>& /*gaussVec*/, Scenario<T>& /*path*/) const
+    {
+        throw std::runtime_error("Model::generatePath(): paths are generated on the GPU, no host evaluation");
+    }
+
+    virtual std::unique_ptr<Model<T>> clone() const = 0;
+    virtual ~Model() {}
+
+    virtual const std::vector<T*>& parameters() = 0;
+    virtual const std::vector<std::string>& parameterLabels() const = 0;
+    size_t numParams() const { return const_cast<Model*>(this)->parameters().size(); }
+
+    void putParametersOnTape()
+    {
+        if constexpr (std::is_same<T, Number>::value)
+            for (Number* param : parameters()) param->putOnTape();
+    }
+
+    // Describe the initialised model (after allocate + init) to the CUDA engine.
+    virtual bool deviceImage(ModelImage& /*img*/, const std::vector<Time>& /*prdTimeline*/,
+                             const std::vector<SampleDef>& /*prdDefline*/) { return false; }
+};
+
+class RNG
+{
+public:
+    virtual void init(const size_t simDim) = 0;
+    virtual void nextU(std::vector<double>& uVec) = 0;
+    virtual void nextG(std::vector<double>& gaussVec) = 0;
+    virtual std::unique_ptr<RNG> clone() const = 0;
+    virtual ~RNG() {}
+    virtual void skipTo(const unsigned b) = 0;
+    // Describe the generator to the CUDA engine.
+    virtual bool deviceImage(cf_rng& /*img*/) const { return false; }
+};
+
+template <class T>
+inline bool checkCompatiblity(const Product<T>& prd, const Model<T>& mdl) { return prd.assetNames() == mdl.assetNames(); }
+
+// ---------------------------------------------------------------------------------------------
+// Engine glue
+// ---------------------------------------------------------------------------------------------
+inline void cfCheck(int rc)
+{
+    if (rc != 0) throw std::runtime_error(cf_last_error());
+}
+
+struct CfDeviceSetup
+{
+    ModelImage   mdl;
+    ProductImage prd;
+    cf_rng       rng{};
+};
+
+template <class T>
+inline void cfBuildImages(const Product<T>& prd, Model<T>& initialisedMdl, const RNG& rng, CfDeviceSetup& s)
+{
+    if (!initialisedMdl.deviceImage(s.mdl, prd.timeline(), prd.defline()))
+        throw std::runtime_error("This model has no device image: it cannot run on the CUDA engine");
+    if (!prd.deviceImage(s.prd, s.mdl))
+        throw std::runtime_error("This product has no device image: it cannot run on the CUDA engine");
+    if (!rng.deviceImage(s.rng))
+        throw std::runtime_error("This RNG has no device image: it cannot run on the CUDA engine");
+}
+
+// Sums only (what main.h actually consumes): payoff sums over paths.
+inline std::vector<double> cfSimulSums(const Product<double>& prd, const Model<double>& mdl, const RNG& rng,
+                                       const size_t nPath, std::vector<double>* perPath = nullptr)
+{
+    if (!checkCompatiblity(prd, mdl)) throw std::runtime_error("Model and product are not compatible");
+    auto cMdl = mdl.clone();
+    cMdl->allocate(prd.timeline(), prd.defline());
+    cMdl->init(prd.timeline(), prd.defline());
+    CfDeviceSetup s;
+    cfBuildImages(prd, *cMdl, rng, s);
+    const size_t nPay = prd.payoffLabels().size();
+    std::vector<double> sums(nPay);
+    if (perPath) perPath->resize(nPath * nPay);
+    cfCheck(cf_run_value(&s.mdl.pod, &s.prd.pod, &s.rng, 0, nPath, sums.data(), perPath ? perPath->data() : nullptr));
+    return sums;
+}
+
+// mcSimul / mcParallelSimul (mcBase.h:267-400): matrix (0..nPath-1, 0..nPay-1) of payoffs
+inline std::vector<std::vector<double>> mcSimul(const Product<double>& prd, const Model<double>& mdl, const RNG& rng,
+                                                const size_t nPath)
+{
+    std::vector<double> flat;
+    cfSimulSums(prd, mdl, rng, nPath, &flat);
+    const size_t nPay = prd.payoffLabels().size();
+    std::vector<std::vector<double>> results(nPath, std::vector<double>(nPay));
+    for (size_t i = 0; i < nPath; ++i) std::copy(flat.begin() + i * nPay, flat.begin() + (i + 1) * nPay, results[i].begin());
+    return results;
+}
+inline std::vector<std::vector<double>> mcParallelSimul(const Product<double>& prd, const Model<double>& mdl,
+                                                        const RNG& rng, const size_t nPath)
+{
+    return mcSimul(prd, mdl, rng, nPath);
+}
+
+// AAD results (mcBase.h:405-422)
+struct AADSimulResults
+{
+    AADSimulResults(const size_t nPath, const size_t nPay, const size_t nParam)
+        : payoffs(nPath, std::vector<double>(nPay)), aggregated(nPath), risks(nParam) {}
+    std::vector<std::vector<double>> payoffs;
+    std::vector<double>              aggregated;
+    std::vector<double>              risks;
+};
+
+// Sums-only AAD results used by the main.h-level entry points
+struct AADSums
+{
+    std::vector<double> payoffSums;
+    double              aggSum = 0.0;
+    std::vector<double> risks;      // already divided by nPath (mcBase.h:745)
+};
+
+const auto defaultAggregator = [](const std::vector<Number>& v) { return v[0]; };
+
+// The aggregators the reference passes (main.h:135, 210-213) are linear in the payoffs; the device
+// takes the weight vector.  Recover it by differentiating aggFun on the host tape at two points and
+// refuse non-linear aggregators loudly.
+template <class F>
+inline std::vector<double> cfAggregatorWeights(const F& aggFun, const size_t nPay)
+{
+    auto gradAt = [&](const double base, const double step) {
+        Tape localTape;
+        Tape* saved = Number::tape;
+        Number::tape = &localTape;
+        std::vector<Number> pays(nPay);
+        for (size_t k = 0; k < nPay; ++k) { pays[k] = Number(base + step * double(k)); pays[k].putOnTape(); }
+        Number result = aggFun(pays);
+        std::vector<double> g(nPay, 0.0);
+        if (result.onTape()) {
+            result.propagateToStart();
+            for (size_t k = 0; k < nPay; ++k) g[k] = pays[k].adjoint();
+        }
+        Number::tape = saved;
+        return g;
+    };
+    const auto g1 = gradAt(1.0, 0.25), g2 = gradAt(3.0, -0.125);
+    for (size_t k = 0; k < nPay; ++k)
+        if (std::fabs(g1[k] - g2[k]) > 1e-12 * (1.0 + std::fabs(g1[k])))
+            throw std::runtime_error("mcSimulAAD: only linear aggregators of the payoffs are supported on the device");
+    return g1;
+}
+
+// Core of mcSimulAAD / mcParallelSimulAAD: tape for the path-independent stage on the host,
+// paths + adjoint sweep on the device, mark-to-start propagation on the host.
+inline AADSums cfSimulAADSums(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng, const size_t nPath,
+                              const std::vector<double>& weights, std::vector<double>* perPathPayoffs = nullptr,
+                              std::vector<double>* perPathAgg = nullptr)
+{
+    if (!checkCompatiblity(prd, mdl)) throw std::runtime_error("Model and product are not compatible");
+    auto cMdl = mdl.clone();
+    cMdl->allocate(prd.timeline(), prd.defline());
+
+    const size_t nPay = prd.payoffLabels().size();
+    const std::vector<Number*>& params = cMdl->parameters();
+    const size_t nParam = params.size();
+
+    // AAD - 1 (mcBase.h:455-472): parameters and init() on tape, then mark
+    Tape& tape = *Number::tape;
+    tape.clear();
+    cMdl->putParametersOnTape();
+    cMdl->init(prd.timeline(), prd.defline());
+    tape.mark();
+
+    CfDeviceSetup s;
+    cfBuildImages(prd, *cMdl, rng, s);
+    const size_t nAdj = cf_table_adjoint_size(&s.mdl.pod, &s.prd.pod);
+    if (nAdj != s.mdl.adjointTargets.size())
+        throw std::runtime_error("mcSimulAAD: device adjoint layout does not match the model's host tables");
+
+    AADSums out;
+    out.payoffSums.resize(nPay);
+    std::vector<double> adj(nAdj);
+    if (perPathPayoffs) perPathPayoffs->resize(nPath * nPay);
+    if (perPathAgg) perPathAgg->resize(nPath);
+    cfCheck(cf_run_aad(&s.mdl.pod, &s.prd.pod, &s.rng, 0, nPath, weights.data(), out.payoffSums.data(), &out.aggSum,
+                       adj.data(), perPathPayoffs ? perPathPayoffs->data() : nullptr,
+                       perPathAgg ? perPathAgg->data() : nullptr));
+
+    // AAD - 4 (mcBase.h:512-527): adjoints accumulated over paths on the pre-mark nodes, one sweep mark -> start
+    for (size_t k = 0; k < nAdj; ++k)
+        if (s.mdl.adjointTargets[k]) s.mdl.adjointTargets[k]->adjoint() += adj[k];
+    Number::propagateMarkToStart();
+    out.risks.resize(nParam);
+    for (size_t j = 0; j < nParam; ++j) out.risks[j] = params[j]->adjoint() / double(nPath);
+    tape.clear();
+    return out;
+}
+
+template <class F = decltype(defaultAggregator)>
+inline AADSimulResults mcSimulAAD(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng,
+                                  const size_t nPath, const F& aggFun = defaultAggregator)
+{
+    const size_t nPay = prd.payoffLabels().size();
+    const auto weights = cfAggregatorWeights(aggFun, nPay);
+    std::vector<double> pp, pa;
+    AADSums sums = cfSimulAADSums(prd, mdl, rng, nPath, weights, &pp, &pa);
+    AADSimulResults results(nPath, nPay, sums.risks.size());
+    for (size_t i = 0; i < nPath; ++i) std::copy(pp.begin() + i * nPay, pp.begin() + (i + 1) * nPay, results.payoffs[i].begin());
+    results.aggregated = std::move(pa);
+    results.risks = std::move(sums.risks);
+    return results;
+}
+
+template <class F = decltype(defaultAggregator)>
+inline AADSimulResults mcParallelSimulAAD(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng,
+                                          const size_t nPath, const F& aggFun = defaultAggregator)
+{
+    return mcSimulAAD(prd, mdl, rng, nPath, aggFun);
+}
+
+// ThreadPool facade (threadPool.h:72-171): the path loops run on the GPU, the pool has nothing to
+// do; kept so that client code starting / resizing the pool (xlExport.cpp:72-81, 1605) still links.
+class ThreadPool
+{
+    size_t myThreads = 0;
+public:
+    static ThreadPool* getInstance() { static ThreadPool instance; return &instance; }
+    size_t numThreads() const { return myThreads; }
+    static size_t threadNum() { return 0; }
+    void start(const size_t nThread = 0) { myThreads = nThread; }
+    void stop() { myThreads = 0; }
+};

@@ -1,0 +1,166 @@
+// cf_main.h -- the entry points of the reference's main.h, same names, arguments and result
+// structs: value (:43-96), AADriskOne (:99-173), AADriskAggregate (:176-254), bumpRisk (:316-359),
+// dupireAADRisk (:364-411).  The simulations behind them run on the CUDA engine; means over paths
+// come from deterministic device reductions instead of std::accumulate over a per-path matrix.
+#pragma once
+
+#include "cf_rng.h"
+#include "cf_store.h"
+
+struct NumericalParam
+{
+    bool parallel;
+    bool useSobol;
+    int  numPath;
+    int  seed1 = 12345;
+    int  seed2 = 1234;
+};
+
+inline std::unique_ptr<RNG> cfMakeRng(const NumericalParam& num)
+{
+    if (num.useSobol) return std::make_unique<Sobol>();
+    return std::make_unique<mrg32k3a>(num.seed1, num.seed2);
+}
+
+struct ValueResults
+{
+    std::vector<std::string> identifiers;
+    std::vector<double>      values;
+};
+
+// Price product in model (main.h:43-77)
+inline ValueResults value(const Model<double>& model, const Product<double>& product, const NumericalParam& num)
+{
+    auto rng = cfMakeRng(num);
+    const auto sums = cfSimulSums(product, model, *rng, size_t(num.numPath));
+    ValueResults results;
+    results.identifiers = product.payoffLabels();
+    results.values.resize(sums.size());
+    for (size_t i = 0; i < sums.size(); ++i) results.values[i] = sums[i] / num.numPath;
+    return results;
+}
+
+inline ValueResults value(const std::string& modelId, const std::string& productId, const NumericalParam& num)
+{
+    const Model<double>* model = getModel<double>(modelId);
+    const Product<double>* product = getProduct<double>(productId);
+    if (!model || !product) throw std::runtime_error("value() : Could not retrieve model and product");
+    return value(*model, *product, num);
+}
+
+struct AADRiskResults
+{
+    std::vector<std::string> payoffIds;
+    std::vector<double>      payoffValues;
+    double                   riskPayoffValue;
+    std::vector<std::string> paramIds;
+    std::vector<double>      risks;
+};
+
+inline AADRiskResults cfAADrisk(const Model<Number>& model, const Product<Number>& product,
+                                const std::vector<double>& weights, const NumericalParam& num)
+{
+    auto rng = cfMakeRng(num);
+    const AADSums sums = cfSimulAADSums(product, model, *rng, size_t(num.numPath), weights);
+    AADRiskResults results;
+    results.payoffIds = product.payoffLabels();
+    results.payoffValues.resize(sums.payoffSums.size());
+    for (size_t i = 0; i < sums.payoffSums.size(); ++i) results.payoffValues[i] = sums.payoffSums[i] / num.numPath;
+    results.riskPayoffValue = sums.aggSum / num.numPath;
+    results.paramIds = model.parameterLabels();
+    results.risks = sums.risks;
+    return results;
+}
+
+// AAD risk, one payoff (main.h:99-173)
+inline AADRiskResults AADriskOne(const std::string& modelId, const std::string& productId, const NumericalParam& num,
+                                 const std::string& riskPayoff = "")
+{
+    const Model<Number>* model = getModel<Number>(modelId);
+    const Product<Number>* product = getProduct<Number>(productId);
+    if (!model || !product) throw std::runtime_error("AADrisk() : Could not retrieve model and product");
+    const std::vector<std::string>& allPayoffs = product->payoffLabels();
+    size_t riskPayoffIdx = 0;
+    if (!riskPayoff.empty()) {
+        auto it = std::find(allPayoffs.begin(), allPayoffs.end(), riskPayoff);
+        if (it == allPayoffs.end()) throw std::runtime_error("AADriskOne() : payoff not found");
+        riskPayoffIdx = size_t(std::distance(allPayoffs.begin(), it));
+    }
+    std::vector<double> weights(allPayoffs.size(), 0.0);
+    weights[riskPayoffIdx] = 1.0;
+    return cfAADrisk(*model, *product, weights, num);
+}
+
+// AAD risk, aggregate portfolio (main.h:176-254)
+inline AADRiskResults AADriskAggregate(const std::string& modelId, const std::string& productId,
+                                       const std::map<std::string, double>& notionals, const NumericalParam& num)
+{
+    const Model<Number>* model = getModel<Number>(modelId);
+    const Product<Number>* product = getProduct<Number>(productId);
+    if (!model || !product) throw std::runtime_error("AADriskAggregate() : Could not retrieve model and product");
+    const std::vector<std::string>& allPayoffs = product->payoffLabels();
+    std::vector<double> vnots(allPayoffs.size(), 0.0);
+    for (const auto& notional : notionals) {
+        auto it = std::find(allPayoffs.begin(), allPayoffs.end(), notional.first);
+        if (it == allPayoffs.end()) throw std::runtime_error("AADriskAggregate() : payoff not found");
+        vnots[size_t(std::distance(allPayoffs.begin(), it))] = notional.second;
+    }
+    return cfAADrisk(*model, *product, vnots, num);
+}
+
+// Values and a matrix of risks, payoffs in columns and parameters in rows (main.h:259-265)
+struct RiskReports
+{
+    std::vector<std::string> payoffs;
+    std::vector<std::string> params;
+    std::vector<double>      values;
+    matrix<double>           risks;
+};
+
+// Bump risk, itemized (main.h:316-359): finite differences by re-running value()
+inline RiskReports bumpRisk(const std::string& modelId, const std::string& productId, const NumericalParam& num)
+{
+    auto* orig = getModel<double>(modelId);
+    const Product<double>* product = getProduct<double>(productId);
+    if (!orig || !product) throw std::runtime_error("bumpRisk() : Could not retrieve model and product");
+    RiskReports results;
+    auto baseRes = value(*orig, *product, num);
+    results.payoffs = baseRes.identifiers;
+    results.values = baseRes.values;
+    auto model = orig->clone();
+    results.params = model->parameterLabels();
+    const std::vector<double*> parameters = model->parameters();
+    const size_t n = parameters.size(), m = results.payoffs.size();
+    results.risks.resize(n, m);
+    for (size_t i = 0; i < n; ++i) {
+        *parameters[i] += 1.e-08;
+        auto bumpRes = value(*model, *product, num);
+        *parameters[i] -= 1.e-08;
+        for (size_t j = 0; j < m; ++j) results.risks[i][j] = 1.0e+08 * (bumpRes.values[j] - baseRes.values[j]);
+    }
+    return results;
+}
+
+struct DupireRiskResults
+{
+    double         value;
+    double         delta;
+    matrix<double> vega;
+};
+
+// Dupire specific: price, delta and vega matrix to the local-vol surface (main.h:364-411)
+inline DupireRiskResults dupireAADRisk(const std::string& modelId, const std::string& productId,
+                                       const std::map<std::string, double>& notionals, const NumericalParam& num)
+{
+    const Model<Number>* model = getModel<Number>(modelId);
+    if (!model) throw std::runtime_error("dupireAADRisk() : Model not found");
+    const Dupire<Number>* dupire = dynamic_cast<const Dupire<Number>*>(model);
+    if (!dupire) throw std::runtime_error("dupireAADRisk() : Model not a Dupire");
+    DupireRiskResults results;
+    auto simulResults = AADriskAggregate(modelId, productId, notionals, num);
+    results.value = simulResults.riskPayoffValue;
+    results.delta = simulResults.risks[0];
+    results.vega.resize(dupire->spots().size(), dupire->times().size());
+    std::copy(std::next(simulResults.risks.begin()), simulResults.risks.end(), results.vega.begin());
+    return results;
+}

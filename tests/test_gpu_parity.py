@@ -1,0 +1,203 @@
+"""GPU parity of the path kernels through the drop-in API (cf_main.h entry points behind
+libcf_host.so) and the low-level C ABI, against (a) committed golden vectors generated from the
+reference and (b) the reference compiled with g++ run live on the same inputs.
+
+Tolerances (BASELINE.json north_star): prices 1e-10 relative, AAD risks 1e-8 relative.  Vega entries
+are compared relatively where |vega| > 1e-6 and absolutely (1e-12) elsewhere: the reference itself
+only reproduces the small entries to ~1e-13 absolute from run to run (thread summation order)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import restate as R
+from conftest import config3_surface, put_config3, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_r1.json")))
+PRICE_TOL, RISK_TOL = 1e-10, 1e-8
+
+
+def check_vega(got, want):
+    got, want = np.asarray(got), np.asarray(want)
+    big = np.abs(want) > 1e-6
+    assert rel_err(got[big], want[big]) < RISK_TOL
+    assert np.max(np.abs(got - want)) < 1e-11
+
+
+# ---- config 1: Black-Scholes European ---------------------------------------------------------
+def test_config1_bs_european(cf):
+    g = GOLD["config1"]
+    cf.put_black_scholes(100, 0.15, False, 0.0, 0.0, "bs1")
+    cf.put_european(100, 1.0, 1.0, "eur1")
+    assert abs(cf.value("bs1", "eur1", g["n"])[0] / g["value"] - 1) < PRICE_TOL
+    assert abs(cf.value("bs1", "eur1", g["n"])[0] / 5.9777943646922012 - 1) < PRICE_TOL     # BASELINE.md pin
+    pv, rv, risks = cf.aad_risk_one("bs1", "eur1", g["n"])
+    assert abs(rv / g["value"] - 1) < PRICE_TOL
+    assert rel_err(risks, g["risks"]) < RISK_TOL
+    assert rel_err(risks[:2], [0.5298707170844229, 39.775613482124662]) < RISK_TOL           # delta, vega pins
+
+
+# ---- config 2: Black-Scholes barrier ----------------------------------------------------------
+@pytest.mark.parametrize("name,sobol", [("config2_sobol", True), ("config2_mrg", False)])
+def test_config2_bs_barrier(cf, name, sobol):
+    g = GOLD[name]
+    cf.put_black_scholes(100, 0.15, False, 0.03, 0.01, "bs2")
+    cf.put_barrier(100, 120, 1.0, 1.0 / 52, 0.01, False, "uoc2")
+    assert rel_err(cf.value("bs2", "uoc2", g["n"], sobol=sobol), g["values"]) < PRICE_TOL
+    pv, rv, risks = cf.aad_risk_one("bs2", "uoc2", g["n"], sobol=sobol)
+    assert rel_err(pv, g["values"]) < PRICE_TOL and abs(rv / g["risk_value"] - 1) < PRICE_TOL
+    assert rel_err(risks, g["risks"]) < RISK_TOL
+
+
+def test_config2_full_size(cf):
+    g = GOLD["config2_full"]
+    cf.put_black_scholes(100, 0.15, False, 0.0, 0.0, "bs1")
+    cf.put_barrier(100, 120, 1.0, 1.0 / 52, 0.01, False, "uoc2")
+    pv, rv, risks = cf.aad_risk_one("bs1", "uoc2", g["n"])
+    assert rel_err(pv, g["values"]) < PRICE_TOL
+    assert rel_err(pv, [2.1240722492984334, 5.9779041811635834]) < PRICE_TOL                 # BASELINE.md pins
+    assert rel_err(risks[:2], g["risks"][:2]) < RISK_TOL
+    assert np.max(np.abs(risks[2:] - np.array(g["risks"][2:]))) < 1e-8 * max(1.0, np.max(np.abs(g["risks"])))
+
+
+# ---- config 3: Dupire barrier, risk to the whole local-vol surface ---------------------------------
+@pytest.mark.parametrize("name,sobol", [("config3_sobol_16k", True), ("config3_mrg_16k", False)])
+def test_config3_dupire_barrier_golden(cf, name, sobol):
+    g = GOLD[name]
+    put_config3(cf, "dup3", "uoc3")
+    assert rel_err(cf.value("dup3", "uoc3", g["n"], sobol=sobol), g["values"]) < PRICE_TOL
+    pp = cf.simul_paths("dup3", "uoc3", 64, sobol=sobol)
+    assert np.max(np.abs(pp - np.array(g["first_paths"]))) < 1e-9
+    val, delta, vega = cf.dupire_aad_risk("dup3", "uoc3", g["notionals"], 30, 36, g["n"], sobol=sobol)
+    assert abs(val / g["value"] - 1) < PRICE_TOL and abs(delta / g["delta"] - 1) < RISK_TOL
+    check_vega(vega, g["vega"])
+
+
+def test_config3_full_size_north_star(cf):
+    """2^20 Sobol paths x 156 steps, 1081 risks: the headline workload, against the reference's own numbers."""
+    g = GOLD["config3_full"]
+    put_config3(cf, "dup3", "uoc3")
+    assert rel_err(cf.value("dup3", "uoc3", g["n"]), g["values"]) < PRICE_TOL
+    val, delta, vega = cf.dupire_aad_risk("dup3", "uoc3", [1.0, 0.0], 30, 36, g["n"])
+    assert abs(val / g["value"] - 1) < PRICE_TOL and abs(val / 0.96926107424976005 - 1) < PRICE_TOL
+    assert abs(delta / g["delta"] - 1) < RISK_TOL and abs(delta / 0.020804057371458962 - 1) < RISK_TOL
+    check_vega(vega, g["vega"])
+    assert abs(vega.sum() / -5.4262407757753115 - 1) < RISK_TOL and abs(vega[13][11] / -0.024065608611340886 - 1) < RISK_TOL
+
+
+def test_dupire_european_and_put_barrier(cf):
+    put_config3(cf, "dup3", "uoc3")
+    cf.put_european(110, 1.0, 1.0, "eur110")
+    g = GOLD["dupire_european_16k"]
+    val, delta, vega = cf.dupire_aad_risk("dup3", "eur110", [1.0], 30, 36, g["n"])
+    assert abs(val / g["value"] - 1) < PRICE_TOL and abs(delta / g["delta"] - 1) < RISK_TOL
+    check_vega(vega, g["vega"])
+    cf.put_barrier(90, 130, 2.0, 1.0 / 12, 0.02, True, "uop")
+    g = GOLD["dupire_uop_mrg_8k"]
+    val, delta, vega = cf.dupire_aad_risk("dup3", "uop", [0.5, 0.5], 30, 36, g["n"], sobol=False)
+    assert abs(val / g["value"] - 1) < PRICE_TOL and abs(delta / g["delta"] - 1) < RISK_TOL
+    check_vega(vega, g["vega"])
+
+
+# ---- live comparison with the compiled reference on odd shapes --------------------------------------
+@pytest.mark.parametrize("n,sobol", [(1, True), (255, True), (257, False), (1000, True), (4097, False)])
+def test_ragged_path_counts_vs_reference(cf, ref, n, sobol):
+    put_config3(cf, "dup3", "uoc3")
+    put_config3(ref, "dup3", "uoc3")
+    assert np.max(np.abs(cf.simul_paths("dup3", "uoc3", n, sobol=sobol) - ref.simul_paths("dup3", "uoc3", n, sobol=sobol))) < 1e-9
+    val, delta, vega = cf.dupire_aad_risk("dup3", "uoc3", [1.0, 0.5], 30, 36, n, sobol=sobol)
+    rval, rdelta, rvega = ref.dupire_aad_risk("dup3", "uoc3", [1.0, 0.5], 30, 36, n, sobol=sobol)
+    assert abs(val - rval) < 1e-10 * max(1.0, abs(rval)) and abs(delta - rdelta) < 1e-8 * max(abs(rdelta), 1e-3)
+    assert np.max(np.abs(vega - rvega)) < 1e-8 * max(np.max(np.abs(rvega)), 1e-3)
+
+
+def test_per_path_aad_results_vs_reference(cf, ref):
+    """mcSimulAAD's per-path outputs (payoffs, aggregated) through the mirrored free function."""
+    cf.put_black_scholes(100, 0.2, False, 0.02, 0.0, "bsx"); ref.put_bs(100, 0.2, False, 0.02, 0.0, "bsx")
+    cf.put_barrier(95, 125, 0.5, 1.0 / 52, 0.01, False, "uocx"); ref.put_barrier(95, 125, 0.5, 1.0 / 52, 0.01, False, "uocx")
+    n = 3000
+    pays, agg, risks = cf.simul_aad_paths("bsx", "uocx", n, risk_payoff=1)
+    rp = ref.simul_paths("bsx", "uocx", n)
+    assert np.max(np.abs(pays - rp)) < 1e-9 and np.max(np.abs(agg - rp[:, 1])) < 1e-9
+    pv, rv, rrisks = ref.aad_risk_one("bsx", "uocx", n, risk_payoff=1)
+    assert rel_err(risks, rrisks) < RISK_TOL
+
+
+def test_deep_out_of_range_spots_flat_extrapolation(cf, ref):
+    """Spot far outside the surface: every path sits in the flat-extrapolation region of interp()."""
+    spots, times, vols = config3_surface()
+    for api in (cf, ref):
+        api.put_dupire(20.0, spots, times, vols, 0.25, "dlow")
+        api.put_dupire(400.0, spots, times, vols, 0.25, "dhigh")
+        api.put_european(20.0, 1.0, 1.0, "e20")
+        api.put_european(380.0, 1.0, 1.0, "e380")
+    for m, p in [("dlow", "e20"), ("dhigh", "e380")]:
+        val, delta, vega = cf.dupire_aad_risk(m, p, [1.0], 30, 36, 2048)
+        rval, rdelta, rvega = ref.dupire_aad_risk(m, p, [1.0], 30, 36, 2048)
+        assert abs(val / rval - 1) < PRICE_TOL and abs(delta / rdelta - 1) < RISK_TOL
+        check_vega(vega, rvega)
+
+
+# ---- low-level C ABI: shards, fallback kernel, determinism --------------------------------------------
+def _config3_lowlevel(eng, time_map=True):
+    spots, times, vols = config3_surface()
+    ptl = R.uoc_timeline(3.0, 1.0 / 52)
+    tab = R.DupireTables(100.0, spots, times, vols, 0.25, ptl)
+    mdl = eng.dupire_model(100.0, tab.log_spots, tab.interp_vols, tab.common, len(ptl),
+                           time_map=tab.time_map() if time_map else None)
+    prd = eng.uoc(120.0, 150.0, float(np.exp(np.log(100.0)) * 0.01), len(ptl))
+    return tab, mdl, prd
+
+
+def test_shards_add_up(eng):
+    """Disjoint skip-ahead blocks (the multi-GPU partition) sum to the single run."""
+    tab, mdl, prd = _config3_lowlevel(eng)
+    n, w = 1 << 15, [1.0, 0.25]
+    for rng in ("sobol", "mrg"):
+        whole = eng.run_aad(mdl, prd, eng.rng(rng), 0, n, w)
+        parts = [eng.run_aad(mdl, prd, eng.rng(rng), k * n // 4, n // 4, w) for k in range(4)]
+        assert abs(sum(p["agg_sum"] for p in parts) / whole["agg_sum"] - 1) < 1e-13
+        tot = sum(p["table_adj"] for p in parts)
+        assert np.max(np.abs(tot - whole["table_adj"])) < 1e-9 * np.max(np.abs(whole["table_adj"]))
+
+
+def test_generic_kernel_matches_fast_kernel(eng):
+    tab, mdl_fast, prd = _config3_lowlevel(eng, True)
+    _, mdl_gen, _ = _config3_lowlevel(eng, False)
+    n, w = 1 << 13, [0.7, 0.3]
+    a = eng.run_aad(mdl_fast, prd, eng.rng("sobol"), 0, n, w)
+    b = eng.run_aad(mdl_gen, prd, eng.rng("sobol"), 0, n, w)
+    assert a["agg_sum"] == pytest.approx(b["agg_sum"], rel=1e-14)
+    _, v = tab.param_risks(b["table_adj"][0], b["table_adj"][1:].reshape(tab.n_steps, -1), 1)
+    assert np.max(np.abs(a["table_adj"][1:].reshape(30, 36) - v)) < 1e-10 * np.max(np.abs(v))
+
+
+def test_bitwise_deterministic(eng):
+    tab, mdl, prd = _config3_lowlevel(eng)
+    a = eng.run_aad(mdl, prd, eng.rng("sobol"), 0, 1 << 16, [1.0, 0.0])
+    b = eng.run_aad(mdl, prd, eng.rng("sobol"), 0, 1 << 16, [1.0, 0.0])
+    assert (a["table_adj"] == b["table_adj"]).all() and a["agg_sum"] == b["agg_sum"] and (a["payoff_sums"] == b["payoff_sums"]).all()
+
+
+def test_aad_matches_bumps(cf):
+    """Independent check of the adjoint kernels: finite differences by re-running value() (bumpRisk, main.h:316)."""
+    cf.put_black_scholes(100, 0.15, False, 0.03, 0.01, "bs2")
+    cf.put_barrier(100, 120, 1.0, 1.0 / 52, 0.05, False, "uocw")
+    n = 1 << 15
+    pv, rv, risks = cf.aad_risk_one("bs2", "uocw", n)
+    values, bumps = cf.bump_risk("bs2", "uocw", n)
+    # the spot is skipped: the smoothing half-width double(S0 * smooth) moves with a spot bump but is, by
+    # design, not differentiated on the tape (mcPrd.h:247), so the reference's AAD delta differs from its bump delta
+    assert np.max(np.abs(bumps[1:, 0] - risks[1:])) < 1e-5 * np.max(np.abs(risks))
+
+
+def test_invalid_descriptors(eng):
+    from compfinance_b200.capi import CfError
+    tab, mdl, prd = _config3_lowlevel(eng)
+    prd_bad = eng.uoc(120.0, 150.0, 1.0, 10)
+    with pytest.raises(CfError, match="event"):
+        eng.run_value(mdl, prd_bad, eng.rng("sobol"), 0, 100)
+    with pytest.raises(CfError, match="n_paths"):
+        eng.run_value(mdl, prd, eng.rng("sobol"), 0, 0)

@@ -1,0 +1,297 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline benchmark of BASELINE.json on N GPUs of one node.
+
+Workload (BASELINE config 3): Dupire local-vol up-and-out barrier call (K 120, B 150,
+3y, weekly monitoring, smoothing 1 %), 30 x 36 local-vol surface, 2^20 Sobol paths x 156 steps,
+value + full AAD risk (delta + 1080 vegas) = dupireAADRisk.  One "step" = one such pricing-and-risk
+pass.  Metric: paths/sec including the full AAD risk (whole job, all GPUs), fp64.
+
+  python bench.py --gpus N --steps K --warmup W            our engine (N > 1: launched under torchrun)
+  python bench.py --impl reference --gpus N ...             the reference's own CPU path (rank 0 only)
+
+N > 1 is STRONG scaling: the 2^20 paths are split into N disjoint skip-ahead blocks, one per rank
+(one process per GPU), and the payoff sums + adjoint vector (1084 doubles) are combined with one NCCL
+all-reduce per step, inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PATHS = 1 << 20
+FLOPS_PER_PATH = 1.63e4          # canonical algorithmic fp64 flops per path incl. AAD
+WORKLOAD = "dupire_uoc_barrier_2^20_sobol_paths_x_156_steps_aad_1081_risks"
+
+
+def config3():
+    spots = np.arange(55, 201, 5.0)
+    times = np.arange(1, 37) / 12.0
+    vols = 0.15 + 0.10 * np.log(spots[:, None] / 100.0) ** 2 + 0.02 * times[None, :]
+    return spots, times, vols
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU, sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(n_paths, repeats=1):
+    """The reference's own multi-threaded CPU path (oracle/_ref: main.h dupireAADRisk ->
+    mcParallelSimulAAD) on the same inputs; returns (paths/sec best of repeats, threads, value, delta)."""
+    from oracle import refapi
+    ref = refapi.get()
+    threads = ref.start_pool(-1) + 1          # workers + the calling thread, the reference's default
+    spots, times, vols = config3()
+    ref.put_dupire(100.0, spots, times, vols, 0.25, "bench_dupire")
+    ref.put_barrier(120.0, 150.0, 3.0, 1.0 / 52, 0.01, False, "bench_uoc")
+    best, out = 1e30, None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = ref.dupire_aad_risk("bench_dupire", "bench_uoc", [1.0, 0.0], 30, 36, n_paths)
+        best = min(best, time.perf_counter() - t0)
+    return n_paths / best, threads, out[0], out[1], best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 1 << 18
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_run(1 << 14)
+    t_tot, pps = 0.0, []
+    for _ in range(args.steps):
+        p, threads, val, delta, secs = cpu_reference_run(sample)
+        pps.append(p); t_tot += secs
+    value = sample * args.steps / t_tot
+    line = {
+        "impl": "reference", "metric": "paths_per_sec_incl_full_aad_risk", "value": value, "unit": "paths/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU path (mcParallelSimulAAD via dupireAADRisk), "
+                   f"each step a bounded sample of {sample} paths of the same workload"},
+        "cpu_baseline": {"value": value, "unit": "paths/s", "cores": threads, "kind": "reference",
+                         "sample": f"{sample} paths x 156 steps per step, {args.steps} steps"},
+        "e2e": {"value": value, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from compfinance_b200 import capi
+    from compfinance_b200.api import CompFinance
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- set-up through the reference-facing host API; the resident plan comes from the same tables
+    cf = CompFinance(device=local_rank)
+    eng = capi.Engine()
+    spots, times, vols = config3()
+    cf.put_dupire(100.0, spots, times, vols, 0.25, "bench_dupire")
+    cf.put_barrier(120.0, 150.0, 3.0, 1.0 / 52, 0.01, False, "bench_uoc")
+    d = cf.describe("bench_dupire", "bench_uoc", aad=True)
+    mdl = eng.dupire_model(100.0, d["tab_b"], d["tab_a"], d["is_event"], d["n_events"], time_map=d["time_map"])
+    prd = eng.uoc(d["strike"], d["barrier"], d["smooth"], d["n_events"])
+    rng = eng.rng("sobol")
+    plan = C.c_void_p()
+    eng._chk(eng.lib.cf_plan_create(C.byref(mdl), C.byref(prd), C.byref(rng), C.byref(plan)))
+    n_out = eng.lib.cf_plan_out_size(plan, 1)
+    d_out = torch.zeros(n_out, dtype=torch.float64, device="cuda")
+    wv = (C.c_double * 2)(1.0, 0.0)
+
+    # strong scaling: disjoint skip-ahead blocks of the 2^20 paths
+    per = N_PATHS // world
+    first, count = rank * per, (per if rank < world - 1 else N_PATHS - per * (world - 1))
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def step():
+        eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first, count, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
+        if world > 1:
+            dist.all_reduce(d_out)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                              # nvidia-smi needs ~0.1 s to deliver its first sample
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    eng._chk(eng.lib.cf_plan_kernel_ms(plan, None, None))       # drop warm-up kernel timings
+    launches0 = eng.lib.cf_launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)                                           # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = eng.lib.cf_launch_count() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = N_PATHS / (ms_per_step * 1e-3)
+    kms, kn = C.c_double(), C.c_int()
+    eng._chk(eng.lib.cf_plan_kernel_ms(plan, C.byref(kms), C.byref(kn)))
+    res = d_out.cpu().numpy()
+    price, delta = res[2] / N_PATHS, res[3] / N_PATHS
+
+    # ---- e2e: the call a user makes (dupireAADRisk through the host API, host buffers in and out)
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = int(d["tab_a"].nbytes + d["tab_b"].nbytes + d["is_event"].nbytes + 4 * 156 * 8 + 32 * 156 * 4 + 2 * 8)
+    d2h = int(n_out * 8)
+
+    def e2e_step():
+        if world == 1:
+            return cf.dupire_aad_risk("bench_dupire", "bench_uoc", [1.0, 0.0], 30, 36, N_PATHS)
+        r = eng.run_aad(mdl, prd, rng, first, count, [1.0, 0.0])          # C ABI, host buffers
+        v = torch.from_numpy(np.concatenate([r["payoff_sums"], [r["agg_sum"]], r["table_adj"]])).pin_memory().cuda(non_blocking=True)
+        dist.all_reduce(v)
+        return v.cpu().numpy()
+
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = N_PATHS * e2e_steps / float(te.item())
+    clocks = sampler.stop()          # sampled under load: warm-up, timed region and the e2e loop
+
+    if rank == 0:
+        fp64_peak = eng.fp64_peak_tflops()
+        achieved = (count / (kms.value * 1e-3)) * FLOPS_PER_PATH / 1e12 if kms.value > 0 else None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "latest_kernel.json")))
+            traffic = prof.get("dram_bytes_per_launch")
+        except OSError:
+            pass
+        roofline = {
+            "bound": "fp64", "kernel": "cf::dupire_kernel<UOC, AAD, Sobol>", "achieved": achieved, "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": achieved / fp64_peak if achieved else None, "traffic": traffic,
+            "kernel_ms": kms.value, "kernel_launches_timed": kn.value,
+            "peak_source": "measured here: scalar DFMA microbenchmark cf_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 entry)",
+            "algorithmic_flops_per_path": FLOPS_PER_PATH,
+            "hbm": {"achieved_gbs": (traffic / (kms.value * 1e-3) / 1e9) if traffic and kms.value > 0 else None,
+                    "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json" if peaks else None},
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                pps, threads, rv, rd, secs = cpu_reference_run(1 << 20, repeats=2)
+                cpu = {"value": pps, "unit": "paths/s", "cores": threads, "kind": "reference",
+                       "sample": "2^20 paths x 156 steps (the full workload), best of 2",
+                       "price_rel_diff_vs_gpu": abs(price / rv - 1), "delta_rel_diff_vs_gpu": abs(delta / rd - 1)}
+            except (OSError, FileNotFoundError) as ex:
+                cpu = {"value": None, "unit": "paths/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+        line = {
+            "metric": "paths_per_sec_incl_full_aad_risk", "value": value, "unit": "paths/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "paths": N_PATHS, "steps_per_path": 156, "surface": "30x36", "rng": "sobol",
+                       "risks": 1081, "parallelism": f"paths sharded over {world} GPU(s), one NCCL all-reduce of {n_out} doubles",
+                       "l2": "flushed between timed iterations (256 MB write)", "price": price, "delta": delta},
+            "clocks": clocks, "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d,
+                                      "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                                      "api": "dupireAADRisk (libcf_host.so)" if world == 1 else "cf_run_aad (C ABI, host buffers) + NCCL all-reduce"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    eng.lib.cf_plan_destroy(plan)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

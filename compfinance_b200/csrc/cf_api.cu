@@ -74,6 +74,14 @@ struct DevBuf {
     }
 };
 
+// Scratch shared by all plans of the process (one run at a time per context): path history,
+// per-block partials, per-warp vol-adjoint tables.  Grown on demand, never shrunk.
+struct Scratch {
+    DevBuf<double> hist, partial, wtab, tmp;
+    void need(DevBuf<double>& b, size_t n) { if (b.n < n) b.alloc(n); }
+};
+Scratch g_scratch;
+
 using KernelFn = void (*)(const cf::KArgs);
 
 template <int MDL, int PRD>
@@ -159,11 +167,9 @@ struct cf_plan {
     bool fast = false, hasTimeMap = false;
     int nTimes = 0;
     DevBuf<int32_t> tk1, tk2;
-    DevBuf<double> tc1, tc2, wtab, scratch;
-    int wtabGrid = 0;
+    DevBuf<double> tc1, tc2;
     cf::DArgs dbase{};
-    DevBuf<double> hist, partial;
-    int histGrid = 0, partialGrid = 0, partialStride = 0;
+    int partialStride = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // recorded since last query
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
 
@@ -196,21 +202,16 @@ struct cf_plan {
         const int grid = std::min(nBatches, 2 * g_sms);
         const size_t tabAdj = mdlKind == CF_MODEL_DUPIRE ? 1 + size_t(D) * m : nAdj;   // generic kernel: table adjoints
         const size_t stride = aad ? size_t(nPay) + 1 + tabAdj : size_t(nPay);
-        if (partialGrid < grid || partialStride < int(stride)) {
-            partial.alloc(size_t(grid) * stride);
-            partialGrid = grid; partialStride = int(stride);
-        }
-        if (aad && histGrid < grid) {
-            hist.alloc(size_t(2) * D * size_t(grid) * cf::kBlock);
-            histGrid = grid;
-        }
+        partialStride = int(stride);
+        g_scratch.need(g_scratch.partial, size_t(grid) * stride);
+        if (aad) g_scratch.need(g_scratch.hist, size_t(2) * D * size_t(grid) * cf::kBlock);
         cf::KArgs a = base;
         a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
         a.w[0] = a.w[1] = 0.0;
         if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
-        a.partial = partial.p; a.partial_stride = partialStride;
+        a.partial = g_scratch.partial.p; a.partial_stride = partialStride;
         a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg;
-        a.hist = hist.p;
+        a.hist = g_scratch.hist.p;
         KernelFn fn = pick(mdlKind, prdKind, aad, rngKind);
         const size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL, lutN);
         if (smem > 227 * 1024) throw CfError("cf_b200: tables do not fit in shared memory (n_steps * n_knots too large)");
@@ -223,14 +224,14 @@ struct cf_plan {
         CF_CUDA(cudaGetLastError());
         if (aad && mdlKind == CF_MODEL_DUPIRE && hasTimeMap) {
             // generic kernel produced interp_vols adjoints: reduce, then apply the time map
-            if (scratch.n < stride) scratch.alloc(stride);
-            cf::reduce_partials_kernel<<<(int(stride) + 127) / 128, 128, 0, s>>>(partial.p, grid, partialStride, int(stride), scratch.p);
+            g_scratch.need(g_scratch.tmp, stride);
+            cf::reduce_partials_kernel<<<(int(stride) + 127) / 128, 128, 0, s>>>(g_scratch.partial.p, grid, partialStride, int(stride), g_scratch.tmp.p);
             const int nOut = int(outSize(true));
-            cf::collapse_time_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(scratch.p, nPay + 2, D, m, nTimes, tk1.p, tk2.p, tc1.p, tc2.p, dOut);
+            cf::collapse_time_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(g_scratch.tmp.p, nPay + 2, D, m, nTimes, tk1.p, tk2.p, tc1.p, tc2.p, dOut);
             g_launches += 1;
         } else {
             const int nOut = int(outSize(aad));
-            cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(partial.p, grid, partialStride, nOut, dOut);
+            cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(g_scratch.partial.p, grid, partialStride, nOut, dOut);
         }
         CF_CUDA(cudaGetLastError());
         g_launches += 2;
@@ -248,23 +249,16 @@ struct cf_plan {
     {
         const int grid = std::min(nBatches, 3 * g_sms);
         const size_t stride = size_t(nPay) + 2;
-        if (partialGrid < grid || partialStride < int(stride)) {
-            partial.alloc(size_t(grid) * stride);
-            partialGrid = grid; partialStride = int(stride);
-        }
-        if (aad && histGrid < grid) {
-            hist.alloc(size_t(storeG ? 2 : 1) * D * size_t(grid) * cf::kBlock);
-            histGrid = grid;
-        }
-        if (aad && wtabGrid < grid) {
-            wtab.alloc(size_t(grid) * cf::kWarps * size_t(nTimes) * m);
-            wtabGrid = grid;
+        g_scratch.need(g_scratch.partial, size_t(grid) * stride);
+        if (aad) {
+            g_scratch.need(g_scratch.hist, size_t(storeG ? 2 : 1) * D * size_t(grid) * cf::kBlock);
+            g_scratch.need(g_scratch.wtab, size_t(grid) * cf::kWarps * size_t(nTimes) * m);
         }
         cf::DArgs a = dbase;
         a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
         a.w[0] = a.w[1] = 0.0;
         if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
-        a.partial = partial.p; a.wtab = wtab.p; a.hist = hist.p;
+        a.partial = g_scratch.partial.p; a.wtab = g_scratch.wtab.p; a.hist = g_scratch.hist.p;
         a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg;
         auto fn = prdKind == CF_PRODUCT_UOC ? pickFast<CF_PRODUCT_UOC>(aad, rngKind) : pickFast<CF_PRODUCT_EUROPEAN>(aad, rngKind);
         const size_t smem = cf::dupire_smem(D, m, dim, rngKind == CF_RNG_SOBOL, lutN, aad).total;
@@ -276,7 +270,15 @@ struct cf_plan {
         events.push_back(ev);
         CF_CUDA(cudaGetLastError());
         const int nOut = int(outSize(aad));
-        cf::dupire_reduce_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(partial.p, grid, nPay, wtab.p, grid * cf::kWarps, m, nTimes, aad ? 1 : 0, dOut);
+        int nChunks = 0;
+        if (aad) {
+            const int nTabs = grid * cf::kWarps, tabLen = nTimes * m;
+            nChunks = (nTabs + cf::kWtabChunk - 1) / cf::kWtabChunk;
+            g_scratch.need(g_scratch.tmp, size_t(nChunks) * tabLen);
+            cf::dupire_wtab_stage1<<<dim3((tabLen + 127) / 128, nChunks), 128, 0, s>>>(g_scratch.wtab.p, nTabs, tabLen, g_scratch.tmp.p);
+            g_launches += 1;
+        }
+        cf::dupire_reduce_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(g_scratch.partial.p, grid, nPay, g_scratch.tmp.p, nChunks, m, nTimes, aad ? 1 : 0, dOut);
         CF_CUDA(cudaGetLastError());
         g_launches += 2;
     }
@@ -540,7 +542,10 @@ int cf_init(int n_devices, const int* device_ids)
 int cf_shutdown(void)
 {
     return guarded([&] {
-        if (g_device >= 0) CF_CUDA(cudaDeviceSynchronize());
+        if (g_device >= 0) {
+            CF_CUDA(cudaDeviceSynchronize());
+            g_scratch.hist.alloc(0); g_scratch.partial.alloc(0); g_scratch.wtab.alloc(0); g_scratch.tmp.alloc(0);
+        }
         g_device = -1;
     });
 }

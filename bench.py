@@ -170,8 +170,8 @@ def main():
     wv = (C.c_double * 2)(1.0, 0.0)
 
     # strong scaling: disjoint skip-ahead blocks of the 2^20 paths
-    per = N_PATHS // world
-    first, count = rank * per, (per if rank < world - 1 else N_PATHS - per * (world - 1))
+    from compfinance_b200.dist import shard_range
+    first, count = shard_range(N_PATHS, rank, world)
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 

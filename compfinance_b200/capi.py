@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcf_b200.so")
+LIB_PATH = os.environ.get("CF_B200_LIB", os.path.join(_HERE, "lib", "libcf_b200.so"))   # override: kernel experiments only
 
 CF_RNG_SOBOL, CF_RNG_MRG32K3A = 0, 1
 CF_MODEL_BS, CF_MODEL_DUPIRE, CF_MODEL_DISPLACED = 0, 1, 2

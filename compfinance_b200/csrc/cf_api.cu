@@ -247,7 +247,7 @@ struct cf_plan {
     void launchFast(bool aad, const double* w, uint64_t first, uint64_t n, int nBatches, double* dOut,
                     double* dPerPath, double* dPerAgg, cudaStream_t s)
     {
-        const int grid = std::min(nBatches, 3 * g_sms);
+        const int grid = std::min(nBatches, CF_DUPIRE_MINBLOCKS * g_sms);
         const size_t stride = size_t(nPay) + 2;
         g_scratch.need(g_scratch.partial, size_t(grid) * stride);
         if (aad) {

@@ -4,9 +4,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -22,6 +24,7 @@ thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 int g_device = -1;
 int g_sms = 0;
+constexpr size_t kFastSmemLimit = 227 * 1024;   // opt-in shared memory per block on sm_100
 
 struct CfError : std::runtime_error { using std::runtime_error::runtime_error; };
 
@@ -77,7 +80,7 @@ struct DevBuf {
 // Scratch shared by all plans of the process (one run at a time per context): path history,
 // per-block partials, per-warp vol-adjoint tables.  Grown on demand, never shrunk.
 struct Scratch {
-    DevBuf<double> hist, partial, wtab, tmp;
+    DevBuf<double> hist, state, partial, partialRev, wtab, btab, tmp;
     void need(DevBuf<double>& b, size_t n) { if (b.n < n) b.alloc(n); }
 };
 Scratch g_scratch;
@@ -168,6 +171,12 @@ struct cf_plan {
     int nTimes = 0;
     DevBuf<int32_t> tk1, tk2;
     DevBuf<double> tc1, tc2;
+    // packed tables of the fast kernel: padded vol rows, buckets, cell records, step bits, time map
+    DevBuf<double> ypad;
+    DevBuf<double2> bk, cells, c12;
+    DevBuf<uint32_t> stepBits;
+    DevBuf<int32_t> k12;
+    int nCells = 0;
     cf::DArgs dbase{};
     int partialStride = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // recorded since last query
@@ -197,7 +206,7 @@ struct cf_plan {
         const uint64_t nb64 = (n + cf::kBlock - 1) / cf::kBlock;
         if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
         const int nBatches = int(nb64);
-        if (fast && (!aad || hasTimeMap)) { launchFast(aad, w, first, n, nBatches, dOut, dPerPath, dPerAgg, s); return; }
+        if (fast && (!aad || hasTimeMap)) { launchFast(aad, w, first, n, dOut, dPerPath, dPerAgg, s); return; }
 
         const int grid = std::min(nBatches, 2 * g_sms);
         const size_t tabAdj = mdlKind == CF_MODEL_DUPIRE ? 1 + size_t(D) * m : nAdj;   // generic kernel: table adjoints
@@ -237,50 +246,86 @@ struct cf_plan {
         g_launches += 2;
     }
 
+    using DKernel = void (*)(const cf::DArgs);
     template <int PRD>
-    static void (*pickFast(bool aad, int rng))(const cf::DArgs)
+    static DKernel pickForward(bool aad, int rng)
     {
-        if (aad) return rng == CF_RNG_SOBOL ? cf::dupire_kernel<PRD, true, CF_RNG_SOBOL> : cf::dupire_kernel<PRD, true, CF_RNG_MRG32K3A>;
-        return rng == CF_RNG_SOBOL ? cf::dupire_kernel<PRD, false, CF_RNG_SOBOL> : cf::dupire_kernel<PRD, false, CF_RNG_MRG32K3A>;
+        if (aad) return rng == CF_RNG_SOBOL ? cf::dupire_forward_kernel<PRD, true, CF_RNG_SOBOL> : cf::dupire_forward_kernel<PRD, true, CF_RNG_MRG32K3A>;
+        return rng == CF_RNG_SOBOL ? cf::dupire_forward_kernel<PRD, false, CF_RNG_SOBOL> : cf::dupire_forward_kernel<PRD, false, CF_RNG_MRG32K3A>;
+    }
+    template <int PRD>
+    static DKernel pickReverse(int P) { return P == 4 ? cf::dupire_reverse_kernel<PRD, 4> : cf::dupire_reverse_kernel<PRD, 2>; }
+
+    // paths per thread of the reverse sweep
+    static int reverseP()
+    {
+        static const int forced = [] { const char* e = std::getenv("CF_DUPIRE_P"); return e ? std::atoi(e) : 0; }();
+        return forced == 4 ? 4 : 2;
     }
 
-    void launchFast(bool aad, const double* w, uint64_t first, uint64_t n, int nBatches, double* dOut,
+    // Runs are cut into launches of at most kFastChunk paths: the log-spot history of one launch is
+    // n_steps * 8 bytes per path (1.3 GB for 2^20 paths x 156 steps).
+    static constexpr uint64_t kFastChunk = 1ull << 21;
+
+    void launchFast(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut,
                     double* dPerPath, double* dPerAgg, cudaStream_t s)
     {
-        const int grid = std::min(nBatches, CF_DUPIRE_MINBLOCKS * g_sms);
-        const size_t stride = size_t(nPay) + 2;
-        g_scratch.need(g_scratch.partial, size_t(grid) * stride);
+        const bool sob = rngKind == CF_RNG_SOBOL;
+        const int P = reverseP();
+        const uint64_t quantum = 256ull * cf::kFwdP;
+        const uint64_t maxChunk = std::min<uint64_t>(n, kFastChunk);
+        const uint64_t maxPad = (maxChunk + quantum - 1) / quantum * quantum;
+        const int maxUnitsF = int(maxPad / quantum) * 8;
+        const int gridF = std::min((maxUnitsF + cf::kFwdWarps - 1) / cf::kFwdWarps, g_sms);
+        const int maxUnitsR = int(maxPad / (32ull * P));
+        const int gridR = std::min((maxUnitsR + cf::kRevWarps - 1) / cf::kRevWarps, g_sms);
+        const size_t tabLen = size_t(nTimes) * m;
+        g_scratch.need(g_scratch.partial, size_t(gridF) * (size_t(nPay) + 1));
         if (aad) {
-            g_scratch.need(g_scratch.hist, size_t(storeG ? 2 : 1) * D * size_t(grid) * cf::kBlock);
-            g_scratch.need(g_scratch.wtab, size_t(grid) * cf::kWarps * size_t(nTimes) * m);
+            g_scratch.need(g_scratch.hist, size_t(D) * maxPad);
+            g_scratch.need(g_scratch.state, 2 * maxPad);
+            g_scratch.need(g_scratch.partialRev, size_t(gridR));
+            g_scratch.need(g_scratch.wtab, size_t(gridR) * cf::kRevWarps * tabLen);
+            g_scratch.need(g_scratch.btab, size_t(gridR) * tabLen);
         }
-        cf::DArgs a = dbase;
-        a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
-        a.w[0] = a.w[1] = 0.0;
-        if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
-        a.partial = g_scratch.partial.p; a.wtab = g_scratch.wtab.p; a.hist = g_scratch.hist.p;
-        a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg;
-        auto fn = prdKind == CF_PRODUCT_UOC ? pickFast<CF_PRODUCT_UOC>(aad, rngKind) : pickFast<CF_PRODUCT_EUROPEAN>(aad, rngKind);
-        const size_t smem = cf::dupire_smem(D, m, dim, rngKind == CF_RNG_SOBOL, lutN, aad).total;
-        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        auto fwd = prdKind == CF_PRODUCT_UOC ? pickForward<CF_PRODUCT_UOC>(aad, rngKind) : pickForward<CF_PRODUCT_EUROPEAN>(aad, rngKind);
+        auto rev = prdKind == CF_PRODUCT_UOC ? pickReverse<CF_PRODUCT_UOC>(P) : pickReverse<CF_PRODUCT_EUROPEAN>(P);
+        const size_t smemF = cf::dupire_smem_fwd<cf::kFwdP>(D, m, dim, sob, nCells).total;
+        const size_t smemR = cf::dupire_smem_rev(D, m, nCells).total;
+        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fwd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
+        if (aad) CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rev), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemR)));
         auto ev = takeEvents();
         CF_CUDA(cudaEventRecord(ev.first, s));
-        fn<<<grid, cf::kBlock, smem, s>>>(a);
+        for (uint64_t off = 0; off < n; off += kFastChunk) {
+            const uint64_t cnt = std::min<uint64_t>(kFastChunk, n - off);
+            cf::DArgs a = dbase;
+            a.first_path = first + off; a.n_paths = cnt;
+            a.n_pad = (cnt + quantum - 1) / quantum * quantum;
+            a.accumulate = off ? 1 : 0;
+            a.w[0] = a.w[1] = 0.0;
+            if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
+            a.partial = g_scratch.partial.p; a.partial_rev = g_scratch.partialRev.p;
+            a.wtab = g_scratch.wtab.p; a.btab = g_scratch.btab.p; a.hist = g_scratch.hist.p; a.state = g_scratch.state.p;
+            a.per_path_payoffs = dPerPath ? dPerPath + off * nPay : nullptr;
+            a.per_path_agg = dPerAgg ? dPerAgg + off : nullptr;
+            a.n_units = int(a.n_pad / quantum) * 8;
+            fwd<<<gridF, cf::kFwdBlock, smemF, s>>>(a);
+            CF_CUDA(cudaGetLastError());
+            ++g_launches;
+            if (aad) {
+                a.n_units = int(a.n_pad / (32ull * P));
+                rev<<<gridR, cf::kRevBlock, smemR, s>>>(a);
+                CF_CUDA(cudaGetLastError());
+                ++g_launches;
+            }
+        }
         CF_CUDA(cudaEventRecord(ev.second, s));
         events.push_back(ev);
-        CF_CUDA(cudaGetLastError());
         const int nOut = int(outSize(aad));
-        int nChunks = 0;
-        if (aad) {
-            const int nTabs = grid * cf::kWarps, tabLen = nTimes * m;
-            nChunks = (nTabs + cf::kWtabChunk - 1) / cf::kWtabChunk;
-            g_scratch.need(g_scratch.tmp, size_t(nChunks) * tabLen);
-            cf::dupire_wtab_stage1<<<dim3((tabLen + 127) / 128, nChunks), 128, 0, s>>>(g_scratch.wtab.p, nTabs, tabLen, g_scratch.tmp.p);
-            g_launches += 1;
-        }
-        cf::dupire_reduce_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(g_scratch.partial.p, grid, nPay, g_scratch.tmp.p, nChunks, m, nTimes, aad ? 1 : 0, dOut);
+        cf::dupire_reduce_kernel<<<(nOut * 32 + 255) / 256, 256, 0, s>>>(g_scratch.partial.p, gridF, nPay, g_scratch.partialRev.p,
+                                                                        g_scratch.btab.p, gridR, m, nTimes, aad ? 1 : 0, dOut);
         CF_CUDA(cudaGetLastError());
-        g_launches += 2;
+        ++g_launches;
     }
 };
 
@@ -364,20 +409,90 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
             p->tc1.upload(mdl->time_w1, size_t(p->D)); p->tc2.upload(mdl->time_w2, size_t(p->D));
             CF_CUDA(cudaStreamSynchronize(nullptr));
         }
-        // the warp-independent kernel needs the bucket LUT, 2..32 knots and a timeline that ends on an event date
-        p->fast = p->lutN > 0 && p->m >= 2 && p->m <= 32 && mdl->is_event[p->D] != 0
-                  && cf::dupire_smem(p->D, p->m, p->dim, rng->kind == CF_RNG_SOBOL, p->lutN, true).total <= 75 * 1024;
-        cf::DArgs& d = p->dbase;
-        d.seed1 = rng->seed1; d.seed2 = rng->seed2; d.dim = p->dim;
-        d.sobol_dir = p->sobolDir.p; d.mrg_jump = p->mrgJump.p;
-        d.n_steps = p->D; d.n_events = p->E; d.n_knots = p->m; d.n_times = p->nTimes;
-        d.is_event = p->isEvent.p; d.spot = mdl->spot;
-        d.interp_vols = p->tabA.p; d.log_spots = p->tabB.p;
-        d.lut = p->lut.p; d.lut_n = p->lutN; d.lut_x0 = p->base.lut_x0; d.lut_scale = p->base.lut_scale;
-        d.store_g = p->storeG;
-        d.k1 = p->tk1.p; d.k2 = p->tk2.p; d.c1 = p->tc1.p; d.c2 = p->tc2.p;
-        d.n_payoffs = prd->n_payoffs; d.is_put = prd->is_put;
-        d.strike = prd->strike; d.barrier = prd->barrier; d.smooth = prd->smooth;
+        // The fast kernel (cf_dupire.cuh) needs: 2..30 knots (32 accumulator slots per lane), vols bounded away
+        // from 0 (g - v is recovered by a division), a timeline that ends on an event date, tables that fit.
+        const int m = p->m, D = p->D;
+        p->fast = m >= 2 && m <= 30 && p->storeG == 0 && mdl->is_event[D] != 0;
+        if (p->fast) {
+            double minDx = 1e300;
+            for (int j = 0; j + 1 < m; ++j) minDx = std::min(minDx, mdl->log_spots[j + 1] - mdl->log_spots[j]);
+            const double x0 = mdl->log_spots[0], range = mdl->log_spots[m - 1] - x0;
+            // uniform cells no wider than half the smallest knot spacing: at most one knot per cell (+ margin)
+            const double width = 0.5 * minDx;
+            const double nc = std::floor(range / width) + 3.0;
+            if (nc > 4096.0) p->fast = false;
+            else {
+                const int nCells = int(nc);
+                const double scale = 1.0 / width;
+                const double delta = 1.0e-9 * width;      // >> rounding of the cell index, << width
+                std::vector<double2> cells;
+                cells.resize(size_t(nCells));
+                for (int c = 0; c < nCells; ++c) {
+                    const double edge = x0 + double(c) * width - delta;
+                    int ub = 0;
+                    while (ub < m && mdl->log_spots[ub] <= edge) ++ub;
+                    double packed = 0.0;
+                    const int64_t bits = int64_t(ub);     // low word = ub0
+                    std::memcpy(&packed, &bits, sizeof(double));
+                    cells[size_t(c)] = make_double2(ub < m ? mdl->log_spots[ub] : DBL_MAX, packed);
+                }
+                p->nCells = nCells;
+                p->cells.upload(cells.data(), cells.size());
+                // padded rows: slot 0 = y[0], slots 1..m = y[0..m-1], slot m+1 = y[m-1]
+                const int SL = m + 2;
+                std::vector<double> ypad;
+                ypad.resize(size_t(D) * SL);
+                for (int i = 0; i < D; ++i) {
+                    const double* y = mdl->interp_vols + size_t(i) * m;
+                    double* r = ypad.data() + size_t(i) * SL;
+                    r[0] = y[0];
+                    for (int j = 0; j < m; ++j) r[j + 1] = y[j];
+                    r[m + 1] = y[m - 1];
+                }
+                p->ypad.upload(ypad.data(), ypad.size());
+                // bucket u = #knots <= L: left knot and 1/width; the two flat buckets have 1/width = 0
+                std::vector<double2> bk;
+                bk.resize(size_t(m) + 1);
+                bk[0] = make_double2(mdl->log_spots[0], 0.0);
+                for (int u = 1; u < m; ++u)
+                    bk[size_t(u)] = make_double2(mdl->log_spots[u - 1], 1.0 / (mdl->log_spots[u] - mdl->log_spots[u - 1]));
+                bk[size_t(m)] = make_double2(mdl->log_spots[m - 1], 0.0);
+                p->bk.upload(bk.data(), bk.size());
+                // event bits of timeline points (the last point is handled outside the loops), flush bits of steps
+                const int nWords = (D + 1 + 31) / 32;
+                std::vector<uint32_t> bits(size_t(2) * nWords, 0u);
+                for (int i = 0; i < D; ++i) {
+                    if (mdl->is_event[i]) bits[size_t(i >> 5)] |= 1u << (i & 31);
+                    const bool fl = p->hasTimeMap && (i == D - 1 || mdl->time_col1[i] != mdl->time_col1[i + 1]
+                                                      || mdl->time_col2[i] != mdl->time_col2[i + 1]);
+                    if (fl) bits[size_t(nWords + (i >> 5))] |= 1u << (i & 31);
+                }
+                p->stepBits.upload(bits.data(), bits.size());
+                std::vector<int32_t> k12(size_t(2) * D, 0);
+                std::vector<double2> c12(size_t(D), make_double2(0.0, 0.0));
+                if (p->hasTimeMap)
+                    for (int i = 0; i < D; ++i) {
+                        k12[size_t(2 * i)] = mdl->time_col1[i]; k12[size_t(2 * i + 1)] = mdl->time_col2[i];
+                        c12[size_t(i)] = make_double2(mdl->time_w1[i], mdl->time_w2[i]);
+                    }
+                p->k12.upload(k12.data(), k12.size());
+                p->c12.upload(c12.data(), c12.size());
+                CF_CUDA(cudaStreamSynchronize(nullptr));
+                const bool sob = rng->kind == CF_RNG_SOBOL;
+                if (cf::dupire_smem_fwd<cf::kFwdP>(D, m, p->dim, sob, nCells).total > kFastSmemLimit
+                    || cf::dupire_smem_rev(D, m, nCells).total > kFastSmemLimit) p->fast = false;
+                cf::DArgs& d = p->dbase;
+                d.seed1 = rng->seed1; d.seed2 = rng->seed2; d.dim = p->dim;
+                d.sobol_dir = p->sobolDir.p; d.mrg_jump = p->mrgJump.p;
+                d.n_steps = D; d.n_knots = m; d.n_slots = SL; d.n_times = p->nTimes;
+                d.step_bits = p->stepBits.p; d.spot = mdl->spot;
+                d.ypad = p->ypad.p; d.bk = p->bk.p; d.cells = p->cells.p; d.n_cells = nCells;
+                d.cell_scale = scale; d.cell_off = -x0 * scale;
+                d.k12 = p->k12.p; d.c12 = p->c12.p;
+                d.n_payoffs = prd->n_payoffs; d.is_put = prd->is_put;
+                d.strike = prd->strike; d.barrier = prd->barrier; d.smooth = prd->smooth;
+            }
+        }
     }
     a.n_payoffs = prd->n_payoffs; a.is_put = prd->is_put;
     a.strike = prd->strike; a.barrier = prd->barrier; a.smooth = prd->smooth;
@@ -544,7 +659,8 @@ int cf_shutdown(void)
     return guarded([&] {
         if (g_device >= 0) {
             CF_CUDA(cudaDeviceSynchronize());
-            g_scratch.hist.alloc(0); g_scratch.partial.alloc(0); g_scratch.wtab.alloc(0); g_scratch.tmp.alloc(0);
+            g_scratch.hist.alloc(0); g_scratch.partial.alloc(0); g_scratch.wtab.alloc(0); g_scratch.btab.alloc(0); g_scratch.tmp.alloc(0);
+            g_scratch.state.alloc(0); g_scratch.partialRev.alloc(0);
         }
         g_device = -1;
     });

@@ -81,6 +81,7 @@ struct DevBuf {
 // per-block partials, per-warp vol-adjoint tables.  Grown on demand, never shrunk.
 struct Scratch {
     DevBuf<double> hist, state, partial, partialRev, wtab, btab, tmp;
+    DevBuf<uint32_t> histU;
     void need(DevBuf<double>& b, size_t n) { if (b.n < n) b.alloc(n); }
 };
 Scratch g_scratch;
@@ -172,10 +173,10 @@ struct cf_plan {
     DevBuf<int32_t> tk1, tk2;
     DevBuf<double> tc1, tc2;
     // packed tables of the fast kernel: padded vol rows, buckets, cell records, step bits, time map
-    DevBuf<double> ypad;
-    DevBuf<double2> bk, cells, c12;
+    DevBuf<double2> ab, bk, cells, c12;
     DevBuf<uint32_t> stepBits;
     DevBuf<int32_t> k12;
+    DevBuf<uint8_t> flushOps;
     int nCells = 0;
     cf::DArgs dbase{};
     int partialStride = 0;
@@ -283,6 +284,7 @@ struct cf_plan {
         g_scratch.need(g_scratch.partial, size_t(gridF) * (size_t(nPay) + 1));
         if (aad) {
             g_scratch.need(g_scratch.hist, size_t(D) * maxPad);
+            if (g_scratch.histU.n < size_t((D + 3) / 4) * maxPad) g_scratch.histU.alloc(size_t((D + 3) / 4) * maxPad);
             g_scratch.need(g_scratch.state, 2 * maxPad);
             g_scratch.need(g_scratch.partialRev, size_t(gridR));
             g_scratch.need(g_scratch.wtab, size_t(gridR) * cf::kRevWarps * tabLen);
@@ -291,7 +293,7 @@ struct cf_plan {
         auto fwd = prdKind == CF_PRODUCT_UOC ? pickForward<CF_PRODUCT_UOC>(aad, rngKind) : pickForward<CF_PRODUCT_EUROPEAN>(aad, rngKind);
         auto rev = prdKind == CF_PRODUCT_UOC ? pickReverse<CF_PRODUCT_UOC>(P) : pickReverse<CF_PRODUCT_EUROPEAN>(P);
         const size_t smemF = cf::dupire_smem_fwd<cf::kFwdP>(D, m, dim, sob, nCells).total;
-        const size_t smemR = cf::dupire_smem_rev(D, m, nCells).total;
+        const size_t smemR = cf::dupire_smem_rev(D, m).total;
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fwd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
         if (aad) CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rev), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemR)));
         auto ev = takeEvents();
@@ -305,7 +307,7 @@ struct cf_plan {
             a.w[0] = a.w[1] = 0.0;
             if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
             a.partial = g_scratch.partial.p; a.partial_rev = g_scratch.partialRev.p;
-            a.wtab = g_scratch.wtab.p; a.btab = g_scratch.btab.p; a.hist = g_scratch.hist.p; a.state = g_scratch.state.p;
+            a.wtab = g_scratch.wtab.p; a.btab = g_scratch.btab.p; a.hist = g_scratch.hist.p; a.hist_u = g_scratch.histU.p; a.state = g_scratch.state.p;
             a.per_path_payoffs = dPerPath ? dPerPath + off * nPay : nullptr;
             a.per_path_agg = dPerAgg ? dPerAgg + off : nullptr;
             a.n_units = int(a.n_pad / quantum) * 8;
@@ -409,18 +411,20 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
             p->tc1.upload(mdl->time_w1, size_t(p->D)); p->tc2.upload(mdl->time_w2, size_t(p->D));
             CF_CUDA(cudaStreamSynchronize(nullptr));
         }
-        // The fast kernel (cf_dupire.cuh) needs: 2..30 knots (32 accumulator slots per lane), vols bounded away
+        // The fast kernels (cf_dupire.cuh) need: 2..30 knots (32 accumulator rows per lane), vols bounded away
         // from 0 (g - v is recovered by a division), a timeline that ends on an event date, tables that fit.
         const int m = p->m, D = p->D;
         p->fast = m >= 2 && m <= 30 && p->storeG == 0 && mdl->is_event[D] != 0;
         if (p->fast) {
+            const double* x = mdl->log_spots;
             double minDx = 1e300;
-            for (int j = 0; j + 1 < m; ++j) minDx = std::min(minDx, mdl->log_spots[j + 1] - mdl->log_spots[j]);
-            const double x0 = mdl->log_spots[0], range = mdl->log_spots[m - 1] - x0;
+            for (int j = 0; j + 1 < m; ++j) minDx = std::min(minDx, x[j + 1] - x[j]);
+            const double shift = 0.5 * (x[0] + x[m - 1]);      // log-spots are carried relative to the centre of the grid
+            const double x0 = x[0] - shift, range = x[m - 1] - x[0];
             // uniform cells no wider than half the smallest knot spacing: at most one knot per cell (+ margin)
             const double width = 0.5 * minDx;
             const double nc = std::floor(range / width) + 3.0;
-            if (nc > 4096.0) p->fast = false;
+            if (nc > 1024.0) p->fast = false;
             else {
                 const int nCells = int(nc);
                 const double scale = 1.0 / width;
@@ -430,65 +434,83 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 for (int c = 0; c < nCells; ++c) {
                     const double edge = x0 + double(c) * width - delta;
                     int ub = 0;
-                    while (ub < m && mdl->log_spots[ub] <= edge) ++ub;
+                    while (ub < m && x[ub] - shift <= edge) ++ub;
                     double packed = 0.0;
                     const int64_t bits = int64_t(ub);     // low word = ub0
                     std::memcpy(&packed, &bits, sizeof(double));
-                    cells[size_t(c)] = make_double2(ub < m ? mdl->log_spots[ub] : DBL_MAX, packed);
+                    cells[size_t(c)] = make_double2(ub < m ? x[ub] - shift : DBL_MAX, packed);
                 }
                 p->nCells = nCells;
                 p->cells.upload(cells.data(), cells.size());
-                // padded rows: slot 0 = y[0], slots 1..m = y[0..m-1], slot m+1 = y[m-1]
-                const int SL = m + 2;
-                std::vector<double> ypad;
-                ypad.resize(size_t(D) * SL);
-                for (int i = 0; i < D; ++i) {
-                    const double* y = mdl->interp_vols + size_t(i) * m;
-                    double* r = ypad.data() + size_t(i) * SL;
-                    r[0] = y[0];
-                    for (int j = 0; j < m; ++j) r[j + 1] = y[j];
-                    r[m + 1] = y[m - 1];
-                }
-                p->ypad.upload(ypad.data(), ypad.size());
-                // bucket u = #knots <= L: left knot and 1/width; the two flat buckets have 1/width = 0
+                // bucket u = #knots <= X: left knot and 1/width; the two flat buckets have 1/width = 0
                 std::vector<double2> bk;
                 bk.resize(size_t(m) + 1);
-                bk[0] = make_double2(mdl->log_spots[0], 0.0);
-                for (int u = 1; u < m; ++u)
-                    bk[size_t(u)] = make_double2(mdl->log_spots[u - 1], 1.0 / (mdl->log_spots[u] - mdl->log_spots[u - 1]));
-                bk[size_t(m)] = make_double2(mdl->log_spots[m - 1], 0.0);
+                bk[0] = make_double2(x[0] - shift, 0.0);
+                for (int u = 1; u < m; ++u) bk[size_t(u)] = make_double2(x[u - 1] - shift, 1.0 / (x[u] - x[u - 1]));
+                bk[size_t(m)] = make_double2(x[m - 1] - shift, 0.0);
                 p->bk.upload(bk.data(), bk.size());
-                // event bits of timeline points (the last point is handled outside the loops), flush bits of steps
-                const int nWords = (D + 1 + 31) / 32;
-                std::vector<uint32_t> bits(size_t(2) * nWords, 0u);
+                // rows of interpVols as per-bucket lines: vol = A + B * X (interp.h:46-62 restated; flat outside)
+                std::vector<double2> ab;
+                ab.resize(size_t(D) * (m + 1));
                 for (int i = 0; i < D; ++i) {
-                    if (mdl->is_event[i]) bits[size_t(i >> 5)] |= 1u << (i & 31);
-                    const bool fl = p->hasTimeMap && (i == D - 1 || mdl->time_col1[i] != mdl->time_col1[i + 1]
-                                                      || mdl->time_col2[i] != mdl->time_col2[i + 1]);
-                    if (fl) bits[size_t(nWords + (i >> 5))] |= 1u << (i & 31);
-                }
-                p->stepBits.upload(bits.data(), bits.size());
-                std::vector<int32_t> k12(size_t(2) * D, 0);
-                std::vector<double2> c12(size_t(D), make_double2(0.0, 0.0));
-                if (p->hasTimeMap)
-                    for (int i = 0; i < D; ++i) {
-                        k12[size_t(2 * i)] = mdl->time_col1[i]; k12[size_t(2 * i + 1)] = mdl->time_col2[i];
-                        c12[size_t(i)] = make_double2(mdl->time_w1[i], mdl->time_w2[i]);
+                    const double* y = mdl->interp_vols + size_t(i) * m;
+                    double2* r = ab.data() + size_t(i) * (m + 1);
+                    r[0] = make_double2(y[0], 0.0);
+                    for (int u = 1; u < m; ++u) {
+                        const double B = (y[u] - y[u - 1]) * bk[size_t(u)].y;
+                        r[u] = make_double2(y[u - 1] - B * bk[size_t(u)].x, B);
                     }
-                p->k12.upload(k12.data(), k12.size());
-                p->c12.upload(c12.data(), c12.size());
+                    r[m] = make_double2(y[m - 1], 0.0);
+                }
+                p->ab.upload(ab.data(), ab.size());
+                // bit i: timeline point i + 1 is an event date (the last point is handled outside the loops)
+                const int nWords = (D + 31) / 32;
+                std::vector<uint32_t> bits(size_t(nWords), 0u);
+                for (int i = 0; i + 1 < D; ++i)
+                    if (mdl->is_event[i + 1]) bits[size_t(i >> 5)] |= 1u << (i & 31);
+                p->stepBits.upload(bits.data(), bits.size());
+                // reverse sweep: which accumulator component holds which time column (simulated in sweep order)
+                std::vector<double2> wxy;
+                wxy.resize(size_t(D));
+                std::vector<int32_t> colxy(size_t(2) * D, 0);
+                std::vector<uint8_t> ops(size_t(D), 0);
+                if (p->hasTimeMap) {
+                    int cx = -1, cy = -1;
+                    for (int i = D - 1; i >= 0; --i) {
+                        const int a1 = mdl->time_col1[i], b1 = mdl->time_col2[i];
+                        const double c1 = mdl->time_w1[i], c2 = mdl->time_w2[i];
+                        if (i == D - 1) { cx = a1; cy = b1; wxy[size_t(i)] = make_double2(c1, c2); }
+                        else {
+                            const int straight = (cx != a1) + (cy != b1), crossed = (cx != b1) + (cy != a1);
+                            if (straight <= crossed) {
+                                ops[size_t(i)] = uint8_t((cx != a1 ? 1 : 0) | (cy != b1 ? 2 : 0));
+                                cx = a1; cy = b1; wxy[size_t(i)] = make_double2(c1, c2);
+                            } else {
+                                ops[size_t(i)] = uint8_t((cx != b1 ? 1 : 0) | (cy != a1 ? 2 : 0));
+                                cx = b1; cy = a1; wxy[size_t(i)] = make_double2(c2, c1);
+                            }
+                        }
+                        colxy[size_t(2 * i)] = cx; colxy[size_t(2 * i + 1)] = cy;
+                    }
+                } else {
+                    for (int i = 0; i < D; ++i) wxy[size_t(i)] = make_double2(0.0, 0.0);
+                }
+                p->c12.upload(wxy.data(), wxy.size());
+                p->k12.upload(colxy.data(), colxy.size());
+                p->flushOps.upload(ops.data(), ops.size());
                 CF_CUDA(cudaStreamSynchronize(nullptr));
                 const bool sob = rng->kind == CF_RNG_SOBOL;
                 if (cf::dupire_smem_fwd<cf::kFwdP>(D, m, p->dim, sob, nCells).total > kFastSmemLimit
-                    || cf::dupire_smem_rev(D, m, nCells).total > kFastSmemLimit) p->fast = false;
+                    || cf::dupire_smem_rev(D, m).total > kFastSmemLimit) p->fast = false;
                 cf::DArgs& d = p->dbase;
                 d.seed1 = rng->seed1; d.seed2 = rng->seed2; d.dim = p->dim;
                 d.sobol_dir = p->sobolDir.p; d.mrg_jump = p->mrgJump.p;
-                d.n_steps = D; d.n_knots = m; d.n_slots = SL; d.n_times = p->nTimes;
-                d.step_bits = p->stepBits.p; d.spot = mdl->spot;
-                d.ypad = p->ypad.p; d.bk = p->bk.p; d.cells = p->cells.p; d.n_cells = nCells;
+                d.n_steps = D; d.n_knots = m; d.n_slots = m + 2; d.n_times = p->nTimes;
+                d.ev_bits = p->stepBits.p; d.ev0 = mdl->is_event[0] ? 1 : 0;
+                d.spot = mdl->spot; d.shift = shift;
+                d.ab = p->ab.p; d.bk = p->bk.p; d.cells = p->cells.p; d.n_cells = nCells;
                 d.cell_scale = scale; d.cell_off = -x0 * scale;
-                d.k12 = p->k12.p; d.c12 = p->c12.p;
+                d.wxy = p->c12.p; d.colxy = p->k12.p; d.flush_ops = p->flushOps.p;
                 d.n_payoffs = prd->n_payoffs; d.is_put = prd->is_put;
                 d.strike = prd->strike; d.barrier = prd->barrier; d.smooth = prd->smooth;
             }
@@ -660,7 +682,7 @@ int cf_shutdown(void)
         if (g_device >= 0) {
             CF_CUDA(cudaDeviceSynchronize());
             g_scratch.hist.alloc(0); g_scratch.partial.alloc(0); g_scratch.wtab.alloc(0); g_scratch.btab.alloc(0); g_scratch.tmp.alloc(0);
-            g_scratch.state.alloc(0); g_scratch.partialRev.alloc(0);
+            g_scratch.state.alloc(0); g_scratch.partialRev.alloc(0); g_scratch.histU.alloc(0);
         }
         g_device = -1;
     });

@@ -3,7 +3,7 @@
 usage: tools/ncu_lines.py report.ncu-rep [top]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-name", "regex:" + __import__("os").environ["NCU_KERNEL"]] if "NCU_KERNEL" in __import__("os").environ else []) + ["--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 fname = None; hdr = None; res = []

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Executed-instruction histogram by SASS opcode. usage: tools/ncu_opcodes.py report.ncu-rep [top]"""
 import csv, subprocess, sys, collections, re
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"] + (["--kernel-name", "regex:" + __import__("os").environ["NCU_KERNEL"]] if "NCU_KERNEL" in __import__("os").environ else []) , capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
 ia, isrc, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed")

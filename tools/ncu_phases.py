@@ -6,7 +6,7 @@ ranges = []
 for a in sys.argv[2:]:
     nm, r = a.split(":"); f, r = (r.split("@") + [None])[:2] if "@" in r else (r, None)
     lo, hi = f.split("-"); ranges.append((nm, int(lo), int(hi), r))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-name", "regex:" + __import__("os").environ["NCU_KERNEL"]] if "NCU_KERNEL" in __import__("os").environ else []) + ["--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 fname = None; hdr = None; res = []
 for r in rows:

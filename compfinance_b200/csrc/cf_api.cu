@@ -261,7 +261,7 @@ struct cf_plan {
     static int reverseP()
     {
         static const int forced = [] { const char* e = std::getenv("CF_DUPIRE_P"); return e ? std::atoi(e) : 0; }();
-        return forced == 4 ? 4 : 2;
+        return forced == 2 ? 2 : 4;
     }
 
     // Runs are cut into launches of at most kFastChunk paths: the log-spot history of one launch is

@@ -8,5 +8,5 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 timeout 600 python bench.py --steps 30 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:dupire_kernel -s 1 -c 1 -o gpurun_out/prof_dupire_aad python scripts/prof_config3.py 1048576 3 aad > gpurun_out/prof_run.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:dupire_ -s 3 -c 2 -f -o gpurun_out/prof_dupire_aad python scripts/prof_config3.py 1048576 3 aad > gpurun_out/prof_run.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json; cat gpurun_out/bench_ref.json

@@ -17,7 +17,8 @@ _ip = C.POINTER(C.c_int)
 
 EXPORTED = [
     "cfx_last_error", "cfx_init", "cfx_set_system_time", "cfx_put_black_scholes", "cfx_put_dupire",
-    "cfx_put_european", "cfx_put_barrier", "cfx_put_europeans", "cfx_num_payoffs", "cfx_num_params",
+    "cfx_put_european", "cfx_put_barrier", "cfx_put_europeans", "cfx_put_displaced", "cfx_put_multistats",
+    "cfx_put_baskets", "cfx_put_autocall", "cfx_num_payoffs", "cfx_num_params",
     "cfx_payoff_labels", "cfx_param_labels", "cfx_product_timeline", "cfx_value", "cfx_simul_paths",
     "cfx_aad_risk_one", "cfx_simul_aad_paths", "cfx_aad_risk_aggregate", "cfx_bump_risk", "cfx_dupire_aad_risk",
     "cfx_describe", "cfx_rng_sequence",
@@ -73,6 +74,28 @@ class CompFinance:
         m, pm = _d(maturities)
         k, pk = _d(strikes)
         self._chk(self.lib.cfx_put_europeans(pm, pk, C.c_int(m.size), id_.encode()))
+
+    def put_displaced(self, spots, atms, skews, disc_rate, repo_spreads, div_dates, divs, correl, lam, id_):
+        """Multi-asset displaced-lognormal model (xPutDLM, xlExport.cpp:186); assets are named a0, a1, ..."""
+        spots, ps = _d(spots); atms, pa = _d(atms); skews, pk = _d(skews); repo, pr = _d(repo_spreads)
+        dd, pdd = _d(div_dates); dv, pdv = _d(divs); co, pc = _d(correl)
+        n = spots.size
+        assert co.shape == (n, n) and (dd.size == 0 or dv.shape == (dd.size, n))
+        self._chk(self.lib.cfx_put_displaced(C.c_int(n), ps, pa, pk, C.c_double(disc_rate), pr, pdd, C.c_int(dd.size), pdv, pc,
+                                             C.c_double(lam), id_.encode()))
+
+    def put_multistats(self, n_assets, fix_dates, fwd_dates, id_):
+        f, pf = _d(fix_dates); w, pw = _d(fwd_dates)
+        self._chk(self.lib.cfx_put_multistats(C.c_int(n_assets), pf, pw, C.c_int(f.size), id_.encode()))
+
+    def put_baskets(self, weights, maturity, strikes, id_):
+        w, pw = _d(weights); k, pk = _d(strikes)
+        self._chk(self.lib.cfx_put_baskets(C.c_int(w.size), pw, C.c_double(maturity), pk, C.c_int(k.size), id_.encode()))
+
+    def put_autocall(self, refs, maturity, periods, ko, strike, cpn, smooth, id_):
+        r, pr = _d(refs)
+        self._chk(self.lib.cfx_put_autocall(C.c_int(r.size), pr, C.c_double(maturity), C.c_int(periods), C.c_double(ko),
+                                            C.c_double(strike), C.c_double(cpn), C.c_double(smooth), id_.encode()))
 
     def num_payoffs(self, product):
         n = self.lib.cfx_num_payoffs(product.encode())

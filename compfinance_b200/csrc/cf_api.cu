@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "cf_dlm.cuh"
 #include "cf_dupire.cuh"
 #include "cf_kernels.cuh"
 #include "cf_tables.h"
@@ -123,19 +124,21 @@ size_t adj_size(const cf_model* mdl)
         return 1 + size_t(mdl->n_steps) * mdl->n_knots;
     }
     if (mdl->kind == CF_MODEL_BS) return 1 + 2 * size_t(mdl->n_steps) + 3 * size_t(mdl->n_events);
+    if (mdl->kind == CF_MODEL_DISPLACED) return size_t(cf::dlm_adj_size(mdl->n_assets, mdl->n_steps, mdl->n_events));
     throw CfError("cf_b200: model kind not implemented");
 }
 
 void validate(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
 {
     if (!mdl || !prd || !rng) throw CfError("cf_b200: null descriptor");
-    if (mdl->n_assets != 1) throw CfError("cf_b200: multi-asset models not implemented yet");
     if (mdl->n_steps < 1 || mdl->n_events < 1) throw CfError("cf_b200: empty timeline");
     if (mdl->n_events != prd->n_events) throw CfError("cf_b200: model and product disagree on the number of event dates");
     if (!mdl->is_event) throw CfError("cf_b200: is_event missing");
     int ev = 0;
     for (int i = 0; i <= mdl->n_steps; ++i) ev += mdl->is_event[i] ? 1 : 0;
     if (ev != mdl->n_events) throw CfError("cf_b200: is_event does not mark n_events points");
+    const bool multi = mdl->kind == CF_MODEL_DISPLACED;
+    if (!multi && mdl->n_assets != 1) throw CfError("cf_b200: Black-Scholes and Dupire are single-asset models");
     if (mdl->kind == CF_MODEL_DUPIRE) {
         if (mdl->n_knots < 1 || !mdl->log_spots || !mdl->interp_vols) throw CfError("cf_b200: Dupire tables missing");
         for (int j = 0; j + 1 < mdl->n_knots; ++j)
@@ -144,10 +147,30 @@ void validate(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
         if (!mdl->bs_drifts || !mdl->bs_stds) throw CfError("cf_b200: Black-Scholes tables missing");
         for (int i = 1; i <= mdl->n_steps; ++i)
             if (!mdl->is_event[i]) throw CfError("cf_b200: every Black-Scholes step must end on an event date");
+    } else if (multi) {
+        if (mdl->n_assets < 1 || mdl->n_assets > 16) throw CfError("cf_b200: the displaced model supports 1 to 16 assets");
+        if (!mdl->dlm_spots || !mdl->dlm_chol || !mdl->dlm_alphas || !mdl->dlm_dynamics || !mdl->dlm_dyn_fwd || !mdl->dlm_drifts
+            || !mdl->dlm_stds || !mdl->dlm_fwd_factors) throw CfError("cf_b200: displaced model tables missing");
+        for (int i = 1; i <= mdl->n_steps; ++i)
+            if (!mdl->is_event[i]) throw CfError("cf_b200: every step of the displaced model must end on an event date");
+        for (int k = 0; k < mdl->n_assets; ++k)
+            if (mdl->dlm_dynamics[k] < 0 || mdl->dlm_dynamics[k] > 3) throw CfError("cf_b200: unknown dynamics");
     } else throw CfError("cf_b200: model kind not implemented");
     if (prd->kind == CF_PRODUCT_EUROPEAN) { if (prd->n_payoffs != 1 || prd->n_events != 1) throw CfError("cf_b200: European has one event and one payoff"); }
     else if (prd->kind == CF_PRODUCT_UOC) { if (prd->n_payoffs != 2) throw CfError("cf_b200: UOC has two payoffs"); if (!(prd->smooth > 0)) throw CfError("cf_b200: UOC smooth must be > 0"); }
-    else throw CfError("cf_b200: product kind not implemented");
+    else if (prd->kind == CF_PRODUCT_AUTOCALL) {
+        if (prd->n_payoffs != 1 || !prd->weights || !prd->event_dt) throw CfError("cf_b200: Autocall needs references, the period length and has one payoff");
+        if (!(prd->smooth > 0) || !(prd->strike > 0)) throw CfError("cf_b200: Autocall smooth and strike must be > 0");
+        if (mdl->is_event[0]) throw CfError("cf_b200: an Autocall has no sample today");
+    } else if (prd->kind == CF_PRODUCT_BASKETS) {
+        if (prd->n_events != 1 || prd->n_payoffs < 1 || !prd->strikes || !prd->weights) throw CfError("cf_b200: Baskets needs weights, strikes and a single event");
+    } else if (prd->kind == CF_PRODUCT_MULTISTATS) {
+        const int A = mdl->n_assets, E = prd->n_events;
+        if (prd->n_payoffs != (2 * E - 1) * (A + A * (A + 1) / 2)) throw CfError("cf_b200: MultiStats payoff count does not match assets and dates");
+    } else throw CfError("cf_b200: product kind not implemented");
+    const bool multiPrd = prd->kind == CF_PRODUCT_AUTOCALL || prd->kind == CF_PRODUCT_BASKETS || prd->kind == CF_PRODUCT_MULTISTATS;
+    if (multi != multiPrd) throw CfError("cf_b200: model/product combination not implemented on the device");
+    if (prd->n_payoffs > 2048) throw CfError("cf_b200: too many payoffs for one product");
     if (rng->kind == CF_RNG_SOBOL) {
         if (mdl->n_steps * mdl->n_assets > cf::sobol_max_dim()) throw CfError("cf_b200: Sobol dimension exceeds 1101");
     } else if (rng->kind != CF_RNG_MRG32K3A) throw CfError("cf_b200: unknown RNG kind");
@@ -179,6 +202,11 @@ struct cf_plan {
     DevBuf<uint8_t> flushOps;
     int nCells = 0;
     cf::DArgs dbase{};
+    // displaced multi-asset model (cf_dlm.cuh)
+    cf::LArgs lbase{};
+    DevBuf<double> lSpots, lChol, lAlphas, lDynFwd, lDrifts, lStds, lFf, lNum, lStrikes, lPw, lW;
+    DevBuf<int32_t> lDyn;
+    int A = 1;
     int partialStride = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // recorded since last query
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
@@ -207,6 +235,7 @@ struct cf_plan {
         const uint64_t nb64 = (n + cf::kBlock - 1) / cf::kBlock;
         if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
         const int nBatches = int(nb64);
+        if (mdlKind == CF_MODEL_DISPLACED) { launchDlm(aad, w, first, n, nBatches, dOut, dPerPath, dPerAgg, s); return; }
         if (fast && (!aad || hasTimeMap)) { launchFast(aad, w, first, n, dOut, dPerPath, dPerAgg, s); return; }
 
         const int grid = std::min(nBatches, 2 * g_sms);
@@ -243,6 +272,58 @@ struct cf_plan {
             const int nOut = int(outSize(aad));
             cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(g_scratch.partial.p, grid, partialStride, nOut, dOut);
         }
+        CF_CUDA(cudaGetLastError());
+        g_launches += 2;
+    }
+
+    using LKernel = void (*)(const cf::LArgs);
+    template <int AMAX, int PRD>
+    static LKernel pickDlm2(bool aad, int rng)
+    {
+        if (aad) {
+            if constexpr (PRD == CF_PRODUCT_MULTISTATS) throw CfError("cf_b200: MultiStats is a value-only test instrument on the device (no AAD)");
+            else return rng == CF_RNG_SOBOL ? cf::dlm_kernel<AMAX, PRD, true, CF_RNG_SOBOL> : cf::dlm_kernel<AMAX, PRD, true, CF_RNG_MRG32K3A>;
+        }
+        return rng == CF_RNG_SOBOL ? cf::dlm_kernel<AMAX, PRD, false, CF_RNG_SOBOL> : cf::dlm_kernel<AMAX, PRD, false, CF_RNG_MRG32K3A>;
+    }
+    template <int AMAX>
+    static LKernel pickDlm(int prd, bool aad, int rng)
+    {
+        if (prd == CF_PRODUCT_AUTOCALL) return pickDlm2<AMAX, CF_PRODUCT_AUTOCALL>(aad, rng);
+        if (prd == CF_PRODUCT_BASKETS) return pickDlm2<AMAX, CF_PRODUCT_BASKETS>(aad, rng);
+        return pickDlm2<AMAX, CF_PRODUCT_MULTISTATS>(aad, rng);
+    }
+
+    void launchDlm(bool aad, const double* w, uint64_t first, uint64_t n, int nBatches, double* dOut, double* dPerPath,
+                   double* dPerAgg, cudaStream_t s)
+    {
+        const int grid = std::min(nBatches, 2 * g_sms);
+        const size_t stride = aad ? size_t(nPay) + 1 + nAdj : size_t(nPay);
+        partialStride = int(stride);
+        g_scratch.need(g_scratch.partial, size_t(grid) * stride);
+        if (aad) g_scratch.need(g_scratch.hist, size_t(D) * (2 * A + 1) * size_t(grid) * cf::kBlock);
+        cf::LArgs a = lbase;
+        a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
+        if (aad) {
+            // the weights are read by the kernel from device memory: stage them on the launch stream
+            CF_CUDA(cudaMemcpyAsync(lW.p, w, sizeof(double) * size_t(nPay), cudaMemcpyHostToDevice, s));
+            CF_CUDA(cudaStreamSynchronize(s));
+        }
+        a.w = lW.p;
+        a.partial = g_scratch.partial.p; a.partial_stride = partialStride;
+        a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg; a.hist = g_scratch.hist.p;
+        LKernel fn = A <= 4 ? pickDlm<4>(prdKind, aad, rngKind) : pickDlm<16>(prdKind, aad, rngKind);
+        const size_t smem = cf::dlm_smem(A, D, E, nPay, dim, rngKind == CF_RNG_SOBOL, aad).total;
+        if (smem > kFastSmemLimit / 2) throw CfError("cf_b200: displaced model tables do not fit in shared memory (n_steps * n_assets or payoffs too large)");
+        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        auto ev = takeEvents();
+        CF_CUDA(cudaEventRecord(ev.first, s));
+        fn<<<grid, cf::kBlock, smem, s>>>(a);
+        CF_CUDA(cudaEventRecord(ev.second, s));
+        events.push_back(ev);
+        CF_CUDA(cudaGetLastError());
+        const int nOut = int(outSize(aad));
+        cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(g_scratch.partial.p, grid, partialStride, nOut, dOut);
         CF_CUDA(cudaGetLastError());
         g_launches += 2;
     }
@@ -343,8 +424,20 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     p->m = mdl->kind == CF_MODEL_DUPIRE ? mdl->n_knots : 0;
     p->nPay = prd->n_payoffs;
     p->nAdj = adj_size(mdl);
+    p->A = mdl->n_assets;
     p->isEvent.upload(mdl->is_event, size_t(p->D) + 1);
-    if (mdl->kind == CF_MODEL_DUPIRE) {
+    if (mdl->kind == CF_MODEL_DISPLACED) {
+        const size_t A = size_t(p->A), D = size_t(p->D), E = size_t(p->E);
+        p->lSpots.upload(mdl->dlm_spots, A); p->lChol.upload(mdl->dlm_chol, A * A); p->lAlphas.upload(mdl->dlm_alphas, A);
+        p->lDyn.upload(mdl->dlm_dynamics, A);
+        p->lDynFwd.upload(mdl->dlm_dyn_fwd, D * A); p->lDrifts.upload(mdl->dlm_drifts, D * A); p->lStds.upload(mdl->dlm_stds, D * A);
+        p->lFf.upload(mdl->dlm_fwd_factors, E * A);
+        if (mdl->numeraires) p->lNum.upload(mdl->numeraires, E);
+        if (prd->strikes && prd->kind == CF_PRODUCT_BASKETS) p->lStrikes.upload(prd->strikes, size_t(prd->n_payoffs));
+        if (prd->weights) p->lPw.upload(prd->weights, A);
+        p->lW.alloc(size_t(prd->n_payoffs));
+        CF_CUDA(cudaMemset(p->lW.p, 0, sizeof(double) * size_t(prd->n_payoffs)));
+    } else if (mdl->kind == CF_MODEL_DUPIRE) {
         p->tabA.upload(mdl->interp_vols, size_t(p->D) * p->m);
         p->tabB.upload(mdl->log_spots, size_t(p->m));
     } else {
@@ -377,7 +470,17 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
             p->base.lut_scale = scale;
         }
     }
-    if (mdl->numeraires) p->num.upload(mdl->numeraires, size_t(p->E));
+    if (mdl->kind == CF_MODEL_DISPLACED) {
+        cf::LArgs& l = p->lbase;
+        l.A = p->A; l.D = p->D; l.E = p->E; l.today = mdl->is_event[0] ? 1 : 0;
+        l.spots = p->lSpots.p; l.chol = p->lChol.p; l.alphas = p->lAlphas.p; l.dyn = p->lDyn.p;
+        l.dynFwd = p->lDynFwd.p; l.drifts = p->lDrifts.p; l.stds = p->lStds.p; l.ff = p->lFf.p; l.num = p->lNum.p;
+        l.n_payoffs = prd->n_payoffs; l.n_strikes = prd->kind == CF_PRODUCT_BASKETS ? prd->n_payoffs : 0;
+        l.strike = prd->strike; l.ko = prd->barrier; l.smooth = prd->smooth; l.coupon = prd->coupon;
+        l.cpn_dt = prd->event_dt ? prd->event_dt[0] : 0.0;
+        l.strikes = p->lStrikes.p; l.pweights = p->lPw.p;
+    }
+    if (mdl->numeraires && mdl->kind != CF_MODEL_DISPLACED) p->num.upload(mdl->numeraires, size_t(p->E));
     if (mdl->fwd_factors) p->ff.upload(mdl->fwd_factors, size_t(p->E));
     if (mdl->discounts) p->disc.upload(mdl->discounts, size_t(p->E));
     if (rng->kind == CF_RNG_SOBOL) {
@@ -395,6 +498,8 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     cf::KArgs& a = p->base;
     a.seed1 = rng->seed1; a.seed2 = rng->seed2; a.dim = p->dim;
     a.sobol_dir = p->sobolDir.p; a.mrg_jump = p->mrgJump.p;
+    p->lbase.seed1 = rng->seed1; p->lbase.seed2 = rng->seed2; p->lbase.dim = p->dim;
+    p->lbase.sobol_dir = p->sobolDir.p; p->lbase.mrg_jump = p->mrgJump.p;
     a.n_steps = p->D; a.n_events = p->E; a.n_knots = p->m;
     a.is_event = p->isEvent.p; a.spot = mdl->spot;
     a.tabA = p->tabA.p; a.tabB = p->tabB.p;

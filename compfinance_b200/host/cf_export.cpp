@@ -93,6 +93,55 @@ int cfx_put_europeans(const double* maturities, const double* strikes, int n, co
     });
 }
 
+// xPutDLM / xPutMultiStats / xPutBaskets / xPutAutocall (xlExport.cpp:186-543); assets are named a0, a1, ...
+static std::vector<std::string> mkNames(int n)
+{
+    std::vector<std::string> v;
+    for (int i = 0; i < n; ++i) v.push_back("a" + std::to_string(i));
+    return v;
+}
+static matrix<double> mkMatrix(const double* data, int rows, int cols)
+{
+    matrix<double> m(rows, cols);
+    if (rows * cols > 0) std::copy(data, data + size_t(rows) * cols, m.begin());
+    return m;
+}
+
+int cfx_put_displaced(int nAssets, const double* spots, const double* atms, const double* skews, double discRate,
+                      const double* repoSpreads, const double* divDates, int nDivs, const double* divs /* [nDivs][nAssets] */,
+                      const double* correl /* [nAssets][nAssets] */, double lambda, const char* id)
+{
+    return guarded([&] {
+        putDisplaced(mkNames(nAssets), std::vector<double>(spots, spots + nAssets), std::vector<double>(atms, atms + nAssets),
+                     std::vector<double>(skews, skews + nAssets), discRate, std::vector<double>(repoSpreads, repoSpreads + nAssets),
+                     std::vector<double>(divDates, divDates + nDivs), mkMatrix(divs, nDivs, nAssets),
+                     mkMatrix(correl, nAssets, nAssets), lambda, id);
+    });
+}
+
+int cfx_put_multistats(int nAssets, const double* fixDates, const double* fwdDates, int n, const char* id)
+{
+    return guarded([&] {
+        putMultiStats(mkNames(nAssets), std::vector<double>(fixDates, fixDates + n), std::vector<double>(fwdDates, fwdDates + n), id);
+    });
+}
+
+int cfx_put_baskets(int nAssets, const double* weights, double maturity, const double* strikes, int nStrikes, const char* id)
+{
+    return guarded([&] {
+        putBaskets(mkNames(nAssets), std::vector<double>(weights, weights + nAssets), maturity,
+                   std::vector<double>(strikes, strikes + nStrikes), id);
+    });
+}
+
+int cfx_put_autocall(int nAssets, const double* refs, double maturity, int periods, double ko, double strike, double cpn,
+                     double smooth, const char* id)
+{
+    return guarded([&] {
+        putAutocall(mkNames(nAssets), std::vector<double>(refs, refs + nAssets), maturity, periods, ko, strike, cpn, smooth, id);
+    });
+}
+
 int cfx_num_payoffs(const char* productId)
 {
     const auto* l = getPayoffLabels(productId);

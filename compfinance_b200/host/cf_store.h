@@ -5,7 +5,9 @@
 #include <unordered_map>
 
 #include "cf_models.h"
+#include "cf_models_multi.h"
 #include "cf_products.h"
+#include "cf_products_multi.h"
 
 using ModelStore = std::unordered_map<std::string, std::pair<std::unique_ptr<Model<double>>, std::unique_ptr<Model<Number>>>>;
 using ProductStore = std::unordered_map<std::string, std::pair<std::unique_ptr<Product<double>>, std::unique_ptr<Product<Number>>>>;
@@ -36,6 +38,15 @@ inline void putDupire(const double spot, const std::vector<double>& spots, const
                       const matrix<double>& vols /* spot major */, const double maxDt, const std::string& store)
 {
     cfPutModel<Dupire>(store, spot, spots, times, vols, maxDt);
+}
+
+// store.h:75-97
+inline void putDisplaced(const std::vector<std::string>& assets, const std::vector<double>& spots, const std::vector<double>& atms,
+                         const std::vector<double>& skews, const double& discRate, const std::vector<double>& repoSpreads,
+                         const std::vector<Time>& divDates, const matrix<double>& divs, const matrix<double>& correl,
+                         const double& lambda, const std::string& store)
+{
+    cfPutModel<MultiDisplaced>(store, assets, discRate, repoSpreads, spots, divDates, divs, atms, skews, correl, lambda);
 }
 
 template <class T> const Model<T>* getModel(const std::string& store);
@@ -76,6 +87,24 @@ inline void putEuropeans(const std::vector<Time>& maturities /* increasing */, c
     std::map<Time, std::vector<double>> options;
     for (size_t i = 0; i < maturities.size(); ++i) options[maturities[i]].push_back(strikes[i]);
     cfPutProduct<Europeans>(store, options);
+}
+
+// store.h:207-255
+inline void putMultiStats(const std::vector<std::string>& assets, const std::vector<Time>& fixDates /* increasing */,
+                          const std::vector<Time>& fwdDates /* on or after the fixings */, const std::string& store)
+{
+    cfPutProduct<MultiStats>(store, assets, fixDates, fwdDates);
+}
+inline void putBaskets(const std::vector<std::string>& assets, const std::vector<double>& weights, const Time maturity,
+                       const std::vector<double> strikes, const std::string& store)
+{
+    cfPutProduct<Baskets>(store, assets, weights, maturity, strikes);
+}
+inline void putAutocall(const std::vector<std::string>& assets, const std::vector<double>& refs, const Time maturity,
+                        const int periods, const double ko, const double strike, const double cpn, const double smooth,
+                        const std::string& store)
+{
+    cfPutProduct<Autocall>(store, assets, refs, maturity, periods, ko, strike, cpn, smooth);
 }
 
 template <class T> const Product<T>* getProduct(const std::string& store);

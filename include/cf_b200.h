@@ -130,7 +130,8 @@ uint64_t cf_launch_count(void);
  *   BS      : 1 (spot) + n_steps (drifts) + n_steps (stds) + 3 * n_events (numeraire, fwd factor, discount)
  *   Dupire  : 1 (spot) + n_steps * n_knots (interp_vols, step-major), or, when the time map is
  *             given, 1 (spot) + n_knots * n_times (vols, spot-major)
- *   Displaced: see cf_b200.h of later rounds (not implemented yet). */
+ *   Displaced: spots [A] | alphas [A] | chol [A][A] (lower) | dyn_fwd [D][A] | drifts [D][A] | stds [D][A] |
+ *             numeraires [E] | fwd_factors [E][A]      (A assets, D steps, E events; cf_dlm.cuh) */
 size_t cf_table_adjoint_size(const cf_model* mdl, const cf_product* prd);
 
 /* ------------------------------------------------------------------------------------------

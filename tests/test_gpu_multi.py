@@ -1,0 +1,102 @@
+"""GPU parity of the multi-asset path (cf_dlm.cuh): MultiDisplaced x {MultiStats, Autocall, Baskets}
+through the drop-in API, against (a) the reference's shipped golden spreadsheets, (b) the reference
+compiled with g++ run live.  Tolerances: prices 1e-10 relative, AAD risks 1e-8 relative (entries below
+1e-6 in absolute value: 1e-12 absolute)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from test_multi_oracle import X, put_dlm, named
+
+pytestmark = pytest.mark.gpu
+PRICE_TOL, RISK_TOL = 1e-10, 1e-8
+
+
+def check_risks(got, want):
+    got, want = np.asarray(got), np.asarray(want)
+    big = np.abs(want) > 1e-6
+    assert rel_err(got[big], want[big]) < RISK_TOL
+    assert np.max(np.abs(got - want)[~big], initial=0.0) < 1e-12
+
+
+def config5(api, model_id="dlm5", product_id="auto5", n_assets=10):
+    a = np.arange(n_assets)
+    spots = 100.0 + 5 * a
+    atms = 0.20 + 0.02 * a
+    skews = np.where(a % 3 == 0, 0.0, -0.05 * (a % 3))
+    correl = np.full((n_assets, n_assets), 0.5) + 0.5 * np.eye(n_assets)
+    api.put_displaced(spots, atms, skews, 0.02, 0.001 * a, [0.5, 1.5], np.full((2, n_assets), 0.01), correl, 0.25, model_id)
+    api.put_autocall(spots, 3.0, 12, 1.0, 0.7, 0.10, 0.01, product_id)
+    return spots
+
+
+def test_shipped_golden_test_dlm_xlsx(cf):
+    """27 moments of the displaced model with dividends, 10^6 Sobol paths (testDLM.xlsx U16:U42)."""
+    g = X["test_dlm"]
+    put_dlm(cf, g, "dlm_t")
+    cf.put_multistats(3, g["fix_dates"], g["fwd_dates"], "stats_t")
+    assert named(cf.payoff_labels("stats_t"), ["google", "amazon", "starbucks"]) == g["labels"]
+    got = cf.value("dlm_t", "stats_t", g["n_paths"])
+    assert rel_err(got, g["values"]) < PRICE_TOL
+
+
+def test_shipped_golden_autocall_pricer_xlsx(cf):
+    """Price and 25 AAD risks of the 3-asset autocallable, 100,000 Sobol paths (AutocallPricer.xlsx R15, R20:R45)."""
+    g = X["autocall_pricer"]
+    put_dlm(cf, g, "dlm_x")
+    cf.put_autocall(g["spots"], g["maturity"], g["periods"], g["ko"], g["strike"], g["cpn"], g["smooth"], "auto_x")
+    assert cf.payoff_labels("auto_x")[0] == g["payoff_label"]
+    assert named(cf.param_labels("dlm_x"), ["uber", "lyft", "luckin"]) == g["risk_labels"]
+    assert abs(cf.value("dlm_x", "auto_x", g["n_paths"])[0] / g["price"] - 1) < PRICE_TOL
+    pv, rv, risks = cf.aad_risk_one("dlm_x", "auto_x", g["n_paths"])
+    assert abs(rv / g["risk_value"] - 1) < PRICE_TOL
+    check_risks(risks, g["risks"])
+
+
+@pytest.mark.parametrize("sobol,n", [(True, 1 << 14), (False, 1 << 14), (False, 4097)])
+def test_config5_autocall_10_assets_vs_reference(cf, ref, sobol, n):
+    config5(cf); config5(ref)
+    want = ref.value("dlm5", "auto5", n, sobol=sobol)
+    assert rel_err(cf.value("dlm5", "auto5", n, sobol=sobol), want) < PRICE_TOL
+    pv, rv, risks = cf.aad_risk_one("dlm5", "auto5", n, sobol=sobol)
+    pv_r, rv_r, risks_r = ref.aad_risk_one("dlm5", "auto5", n, sobol=sobol)
+    assert abs(rv / rv_r - 1) < PRICE_TOL
+    assert risks.size == 107
+    check_risks(risks, risks_r)
+
+
+def test_per_path_payoffs_autocall(cf, ref):
+    config5(cf); config5(ref)
+    got = cf.simul_paths("dlm5", "auto5", 777, sobol=False)
+    want = ref.simul_paths("dlm5", "auto5", 777, sobol=False)
+    assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_baskets_vs_reference(cf, ref):
+    """Strike ladder on a weighted basket of 4 assets with all four dynamics, value + aggregate AAD risk."""
+    spots = [100.0, 50.0, 80.0, 120.0]
+    atms = [0.2, 0.3, 0.25, 0.2]
+    skews = [0.0, -0.15, -0.1, 0.02]          # lognormal, normal (beta = 0), surnormal, surnormal
+    correl = np.array([[1, .4, .2, .1], [.4, 1, .3, .0], [.2, .3, 1, -.2], [.1, .0, -.2, 1]])
+    strikes = np.arange(60.0, 121.0, 5.0)
+    for api in (cf, ref):
+        api.put_displaced(spots, atms, skews, 0.03, [0.0, 0.005, 0.0, 0.01], [0.3], [[0.02, 0.0, 0.01, 0.0]], correl, 0.1, "dlm4")
+        api.put_baskets([0.25, 0.5, 0.3125, 0.2], 1.0, strikes, "bsk")
+    n = 1 << 14
+    assert rel_err(cf.value("dlm4", "bsk", n), ref.value("dlm4", "bsk", n)) < PRICE_TOL
+    notionals = np.linspace(1.0, 2.0, strikes.size)
+    pv, rv, risks = cf.aad_risk_aggregate("dlm4", "bsk", notionals, n, sobol=False)
+    pv_r, rv_r, risks_r = ref.aad_risk_aggregate("dlm4", "bsk", notionals, n, sobol=False)
+    assert rel_err(pv, pv_r) < PRICE_TOL and abs(rv / rv_r - 1) < PRICE_TOL
+    check_risks(risks, risks_r)
+
+
+def test_multistats_has_no_device_aad(cf):
+    g = X["test_dlm"]
+    put_dlm(cf, g, "dlm_t")
+    cf.put_multistats(3, g["fix_dates"], g["fwd_dates"], "stats_t")
+    with pytest.raises(RuntimeError):
+        cf.aad_risk_one("dlm_t", "stats_t", 1024)

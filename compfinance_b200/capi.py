@@ -69,6 +69,8 @@ def load():
                                  C.c_uint64, _dp, _dp]
     lib.cf_run_aad.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product), C.POINTER(cf_rng), C.c_uint64,
                                C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.cf_run_aad_multi.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product), C.POINTER(cf_rng), C.c_uint64,
+                                     C.c_uint64, _dp, _dp]
     lib.cf_sobol_states.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
     lib.cf_rng_draw.argtypes = [C.POINTER(cf_rng), C.c_int, C.c_uint64, C.c_uint64, C.c_int, _dp]
     lib.cf_mrg_numerators.argtypes = [C.POINTER(cf_rng), C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
@@ -79,7 +81,7 @@ def load():
 
 EXPORTED = [
     "cf_init", "cf_shutdown", "cf_last_error", "cf_launch_count", "cf_table_adjoint_size", "cf_run_value",
-    "cf_run_aad", "cf_plan_create", "cf_plan_destroy", "cf_plan_launch_value", "cf_plan_launch_aad",
+    "cf_run_aad", "cf_run_aad_multi", "cf_plan_create", "cf_plan_destroy", "cf_plan_launch_value", "cf_plan_launch_aad",
     "cf_plan_out_size", "cf_plan_kernel_ms", "cf_sobol_states", "cf_sobol_direction_number", "cf_sobol_max_dim",
     "cf_rng_draw", "cf_mrg_numerators", "cf_inv_normal", "cf_measure_fp64_peak", "cf_device_sm_count",
 ]

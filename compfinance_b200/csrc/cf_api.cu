@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "cf_dlm.cuh"
+#include "cf_multi.cuh"
 #include "cf_dupire.cuh"
 #include "cf_kernels.cuh"
 #include "cf_tables.h"
@@ -104,16 +105,18 @@ KernelFn pick(int mdl, int prd, bool aad, int rng)
     if (mdl == CF_MODEL_BS && prd == CF_PRODUCT_UOC) return pick2<CF_MODEL_BS, CF_PRODUCT_UOC>(aad, rng);
     if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_EUROPEAN) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_EUROPEAN>(aad, rng);
     if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_UOC) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_UOC>(aad, rng);
+    if (mdl == CF_MODEL_BS && prd == CF_PRODUCT_EUROPEANS) return pick2<CF_MODEL_BS, CF_PRODUCT_EUROPEANS>(aad, rng);
+    if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_EUROPEANS) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_EUROPEANS>(aad, rng);
     throw CfError("cf_b200: model/product combination not implemented on the device");
 }
 
-size_t smem_for(int mdl, bool aad, int D, int m, int E, int dim, bool sobol, int lutN)
+size_t smem_for(int mdl, bool aad, int D, int m, int E, int dim, bool sobol, int lutN, int nPayRows)
 {
     if (mdl == CF_MODEL_DUPIRE)
-        return aad ? cf::smem_sizes<CF_MODEL_DUPIRE, true>(D, m, E, dim, sobol, lutN).total
-                   : cf::smem_sizes<CF_MODEL_DUPIRE, false>(D, m, E, dim, sobol, lutN).total;
-    return aad ? cf::smem_sizes<CF_MODEL_BS, true>(D, m, E, dim, sobol, lutN).total
-               : cf::smem_sizes<CF_MODEL_BS, false>(D, m, E, dim, sobol, lutN).total;
+        return aad ? cf::smem_sizes<CF_MODEL_DUPIRE, true>(D, m, E, dim, sobol, lutN, nPayRows).total
+                   : cf::smem_sizes<CF_MODEL_DUPIRE, false>(D, m, E, dim, sobol, lutN, nPayRows).total;
+    return aad ? cf::smem_sizes<CF_MODEL_BS, true>(D, m, E, dim, sobol, lutN, nPayRows).total
+               : cf::smem_sizes<CF_MODEL_BS, false>(D, m, E, dim, sobol, lutN, nPayRows).total;
 }
 
 size_t adj_size(const cf_model* mdl)
@@ -158,6 +161,12 @@ void validate(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
     } else throw CfError("cf_b200: model kind not implemented");
     if (prd->kind == CF_PRODUCT_EUROPEAN) { if (prd->n_payoffs != 1 || prd->n_events != 1) throw CfError("cf_b200: European has one event and one payoff"); }
     else if (prd->kind == CF_PRODUCT_UOC) { if (prd->n_payoffs != 2) throw CfError("cf_b200: UOC has two payoffs"); if (!(prd->smooth > 0)) throw CfError("cf_b200: UOC smooth must be > 0"); }
+    else if (prd->kind == CF_PRODUCT_EUROPEANS) {
+        if (!prd->strikes || !prd->strike_offsets || prd->n_payoffs < 1) throw CfError("cf_b200: Europeans needs strikes and their offsets per event");
+        if (prd->strike_offsets[0] != 0 || prd->strike_offsets[prd->n_events] != prd->n_payoffs) throw CfError("cf_b200: Europeans strike offsets do not cover the payoffs");
+        for (int e = 0; e < prd->n_events; ++e)
+            if (prd->strike_offsets[e + 1] < prd->strike_offsets[e]) throw CfError("cf_b200: Europeans strike offsets must not decrease");
+    }
     else if (prd->kind == CF_PRODUCT_AUTOCALL) {
         if (prd->n_payoffs != 1 || !prd->weights || !prd->event_dt) throw CfError("cf_b200: Autocall needs references, the period length and has one payoff");
         if (!(prd->smooth > 0) || !(prd->strike > 0)) throw CfError("cf_b200: Autocall smooth and strike must be > 0");
@@ -204,6 +213,8 @@ struct cf_plan {
     cf::DArgs dbase{};
     // displaced multi-asset model (cf_dlm.cuh)
     cf::LArgs lbase{};
+    DevBuf<double> eStrikes;
+    DevBuf<int32_t> eOff;
     DevBuf<double> lSpots, lChol, lAlphas, lDynFwd, lDrifts, lStds, lFf, lNum, lStrikes, lPw, lW;
     DevBuf<int32_t> lDyn;
     int A = 1;
@@ -248,11 +259,16 @@ struct cf_plan {
         a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
         a.w[0] = a.w[1] = 0.0;
         if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
+        if (aad && prdKind == CF_PRODUCT_EUROPEANS) {
+            CF_CUDA(cudaMemcpyAsync(lW.p, w, sizeof(double) * size_t(nPay), cudaMemcpyHostToDevice, s));
+            CF_CUDA(cudaStreamSynchronize(s));
+        }
+        a.wlong = lW.p;
         a.partial = g_scratch.partial.p; a.partial_stride = partialStride;
         a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg;
         a.hist = g_scratch.hist.p;
         KernelFn fn = pick(mdlKind, prdKind, aad, rngKind);
-        const size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL, lutN);
+        const size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL, lutN, prdKind == CF_PRODUCT_EUROPEANS ? nPay : 0);
         if (smem > 227 * 1024) throw CfError("cf_b200: tables do not fit in shared memory (n_steps * n_knots too large)");
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         auto ev = takeEvents();
@@ -480,6 +496,12 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
         l.cpn_dt = prd->event_dt ? prd->event_dt[0] : 0.0;
         l.strikes = p->lStrikes.p; l.pweights = p->lPw.p;
     }
+    if (prd->kind == CF_PRODUCT_EUROPEANS) {
+        p->eStrikes.upload(prd->strikes, size_t(prd->n_payoffs));
+        p->eOff.upload(prd->strike_offsets, size_t(prd->n_events) + 1);
+        p->lW.alloc(size_t(prd->n_payoffs));
+        CF_CUDA(cudaMemset(p->lW.p, 0, sizeof(double) * size_t(prd->n_payoffs)));
+    }
     if (mdl->numeraires && mdl->kind != CF_MODEL_DISPLACED) p->num.upload(mdl->numeraires, size_t(p->E));
     if (mdl->fwd_factors) p->ff.upload(mdl->fwd_factors, size_t(p->E));
     if (mdl->discounts) p->disc.upload(mdl->discounts, size_t(p->E));
@@ -623,6 +645,8 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     }
     a.n_payoffs = prd->n_payoffs; a.is_put = prd->is_put;
     a.strike = prd->strike; a.barrier = prd->barrier; a.smooth = prd->smooth;
+    a.strikes = p->eStrikes.p; a.strike_off = p->eOff.p;
+    if (prd->kind == CF_PRODUCT_EUROPEANS) p->fast = false;      // many payoffs: generic kernel
     return p;
 }
 
@@ -887,6 +911,106 @@ int cf_run_aad(const cf_model* mdl, const cf_product* prd, const cf_rng* rng, ui
         if (per_path_payoffs)
             CF_CUDA(cudaMemcpy(per_path_payoffs, dPer.p, sizeof(double) * n_paths * plan->nPay, cudaMemcpyDeviceToHost));
         if (per_path_agg) CF_CUDA(cudaMemcpy(per_path_agg, dAgg.p, sizeof(double) * n_paths, cudaMemcpyDeviceToHost));
+        CF_CUDA(cudaDeviceSynchronize());
+    });
+}
+
+int cf_run_aad_multi(const cf_model* mdl, const cf_product* prd, const cf_rng* rng, uint64_t first_path,
+                     uint64_t n_paths, double* payoff_sums, double* risk_tables)
+{
+    return guarded([&] {
+        if (!payoff_sums || !risk_tables) throw CfError("cf_run_aad_multi: null output");
+        auto plan = make_plan(mdl, prd, rng);
+        const int nPay = plan->nPay;
+        const size_t nAdj = plan->nAdj;
+        if (n_paths == 0) throw CfError("cf_b200: n_paths must be > 0");
+        const bool special = mdl->kind == CF_MODEL_DUPIRE && prd->kind == CF_PRODUCT_EUROPEANS && plan->hasTimeMap
+                             && plan->D <= cf::kMultiMaxSteps;
+        if (!special) {
+            // one adjoint sweep per payoff: column k of the risk matrix is the aggregate risk with weights e_k
+            if (nPay > 64) throw CfError("cf_run_aad_multi: this model / product pair has too many payoffs for itemised risk on the device");
+            DevBuf<double> dOut;
+            const size_t nOut = plan->outSize(true);
+            dOut.alloc(nOut);
+            std::vector<double> h(nOut), w(size_t(nPay), 0.0);
+            for (int k = 0; k < nPay; ++k) {
+                std::fill(w.begin(), w.end(), 0.0);
+                w[size_t(k)] = 1.0;
+                plan->launch(true, w.data(), first_path, n_paths, dOut.p, nullptr, nullptr, nullptr);
+                CF_CUDA(cudaMemcpy(h.data(), dOut.p, sizeof(double) * nOut, cudaMemcpyDeviceToHost));
+                if (k == 0) std::memcpy(payoff_sums, h.data(), sizeof(double) * size_t(nPay));
+                for (size_t q = 0; q < nAdj; ++q) risk_tables[q * size_t(nPay) + size_t(k)] = h[size_t(nPay) + 1 + q];
+            }
+            CF_CUDA(cudaDeviceSynchronize());
+            return;
+        }
+        // ---- Dupire x Europeans: one sweep per maturity, accumulated by strike class (cf_multi.cuh)
+        const int D = plan->D, m = plan->m, E = plan->E, nTimes = plan->nTimes;
+        if (plan->rngKind == CF_RNG_SOBOL && first_path + n_paths > 0xffffffffull) throw CfError("cf_b200: Sobol index exceeds 2^32 - 1");
+        std::vector<double> ksorted(static_cast<size_t>(nPay));
+        std::vector<int32_t> payEvent(static_cast<size_t>(nPay)), payRank(static_cast<size_t>(nPay)), payOrig(static_cast<size_t>(nPay));
+        int cmax = 1;
+        for (int e = 0; e < E; ++e) {
+            const int k0 = prd->strike_offsets[e], k1 = prd->strike_offsets[e + 1];
+            std::vector<int> order;
+            for (int k = k0; k < k1; ++k) order.push_back(k);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return prd->strikes[x] < prd->strikes[y]; });
+            for (int r = 0; r < k1 - k0; ++r) {
+                ksorted[size_t(k0 + r)] = prd->strikes[order[size_t(r)]];
+                payEvent[size_t(k0 + r)] = e; payRank[size_t(k0 + r)] = r; payOrig[size_t(k0 + r)] = order[size_t(r)];
+            }
+            cmax = std::max(cmax, k1 - k0 + 1);
+        }
+        // class of a path = #strikes strictly below S_e; a payoff is in the money for classes above the position of
+        // the LAST strike equal to its own
+        for (int e = 0; e < E; ++e) {
+            const int k0 = prd->strike_offsets[e], k1 = prd->strike_offsets[e + 1];
+            for (int r = 0; r < k1 - k0; ++r) {
+                int last = r;
+                while (last + 1 < k1 - k0 && ksorted[size_t(k0 + last + 1)] == ksorted[size_t(k0 + r)]) ++last;
+                payRank[size_t(k0 + r)] = last;
+            }
+        }
+        const size_t tabLen = 1 + size_t(D) * m;
+        DevBuf<double> dK, dT, dPartial, dSums, dOut;
+        DevBuf<int32_t> dEv, dRank, dOrig;
+        dK.upload(ksorted.data(), ksorted.size());
+        dEv.upload(payEvent.data(), payEvent.size()); dRank.upload(payRank.data(), payRank.size()); dOrig.upload(payOrig.data(), payOrig.size());
+        dT.alloc(size_t(E) * cmax * tabLen);
+        CF_CUDA(cudaMemset(dT.p, 0, sizeof(double) * dT.n));
+        const uint64_t nb64 = (n_paths + cf::kBlock - 1) / cf::kBlock;
+        if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
+        const int grid = int(std::min<uint64_t>(nb64, uint64_t(2) * g_sms));
+        dPartial.alloc(size_t(grid) * nPay);
+        dSums.alloc(size_t(nPay));
+        cf::MArgs a{};
+        a.first_path = first_path; a.n_paths = n_paths; a.n_batches = int(nb64);
+        a.seed1 = rng->seed1; a.seed2 = rng->seed2; a.dim = plan->dim;
+        a.sobol_dir = plan->sobolDir.p; a.mrg_jump = plan->mrgJump.p;
+        a.D = D; a.m = m; a.E = E; a.is_event = plan->isEvent.p; a.spot = mdl->spot;
+        a.interp_vols = plan->tabA.p; a.log_spots = plan->tabB.p;
+        a.ksorted = dK.p; a.koff = plan->eOff.p; a.n_payoffs = nPay; a.cmax = cmax;
+        a.partial = dPartial.p; a.T = dT.p; a.per_path_payoffs = nullptr;
+        const bool sob = plan->rngKind == CF_RNG_SOBOL;
+        const size_t smem = cf::multi_smem(D, m, nPay, plan->dim, sob).total;
+        if (smem > kFastSmemLimit / 2) throw CfError("cf_run_aad_multi: tables do not fit in shared memory");
+        auto fn = sob ? cf::dupire_europeans_multi_kernel<CF_RNG_SOBOL> : cf::dupire_europeans_multi_kernel<CF_RNG_MRG32K3A>;
+        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        fn<<<grid, cf::kBlock, smem>>>(a);
+        CF_CUDA(cudaGetLastError());
+        cf::reduce_partials_kernel<<<(nPay + 127) / 128, 128>>>(dPartial.p, grid, nPay, nPay, dSums.p);
+        const size_t nSuffix = size_t(E) * tabLen;
+        cf::multi_suffix_kernel<<<unsigned((nSuffix + 255) / 256), 256>>>(dT.p, E, cmax, tabLen);
+        const size_t nParam = 1 + size_t(m) * nTimes;
+        dOut.alloc(nParam * nPay);
+        cf::multi_collapse_kernel<<<unsigned((nParam * nPay + 255) / 256), 256>>>(dT.p, E, cmax, D, m, nTimes, plan->tk1.p, plan->tk2.p,
+                                                                                 plan->tc1.p, plan->tc2.p, dEv.p, dRank.p, dOrig.p, nPay, dOut.p);
+        CF_CUDA(cudaGetLastError());
+        g_launches += 4;
+        std::vector<double> sums(static_cast<size_t>(nPay));
+        CF_CUDA(cudaMemcpy(sums.data(), dSums.p, sizeof(double) * size_t(nPay), cudaMemcpyDeviceToHost));
+        for (int ps = 0; ps < nPay; ++ps) payoff_sums[payOrig[size_t(ps)]] = sums[size_t(ps)];
+        CF_CUDA(cudaMemcpy(risk_tables, dOut.p, sizeof(double) * nParam * nPay, cudaMemcpyDeviceToHost));
         CF_CUDA(cudaDeviceSynchronize());
     });
 }

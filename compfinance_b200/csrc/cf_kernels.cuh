@@ -56,6 +56,10 @@ struct KArgs {
     int      n_payoffs, is_put;
     double   strike, barrier, smooth;
     double   w[kMaxPay];           // payoff weights of the aggregate (AAD)
+    // Europeans (mcPrd.h:290-401): strikes of event e are strikes[strike_off[e] .. strike_off[e+1]), weights in memory
+    const double*  strikes;
+    const int32_t* strike_off;
+    const double*  wlong;          // [n_payoffs] payoff weights of the aggregate (AAD), device memory
     // outputs
     double*  partial;              // [gridDim][partial_stride]: payoff sums, agg, table adjoints
     int      partial_stride;
@@ -90,6 +94,25 @@ struct FwdSrc {          // Black-Scholes: forward = S * ff[e], numeraire / disc
 };
 struct SampleAdj { double fwd, num, disc; };
 
+// Sink for products with many payoffs (Europeans): payoff k of this path goes to the warp's row of payoff
+// sums (fixed order: lanes by shuffle tree, warps combined at the end of the kernel), to the aggregate
+// and, on request, to the per-path matrix.
+struct PayCtx {
+    double*       myPay;       // this warp's [n_payoffs] row in shared memory
+    const double* w;           // aggregate weights or null
+    double*       perPath;     // this path's [n_payoffs] row or null
+    double        agg;
+    bool          valid;
+    int           lane;
+    __device__ __forceinline__ void emit(int k, double v)
+    {
+        const double s = warp_sum(valid ? v : 0.0);
+        if (lane == 0) myPay[k] += s;
+        if (w) agg += __ldg(w + k) * v;
+        if (perPath) perPath[k] = v;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Products (streaming form: one call per event date, in order)
 // ---------------------------------------------------------------------------------------------
@@ -99,7 +122,7 @@ template <int PRD> struct Product;
 template <> struct Product<CF_PRODUCT_EUROPEAN> {
     double strike, pay, wbar;
     __device__ void init(const KArgs& a) { strike = a.strike; pay = 0.0; }
-    template <class Src> __device__ void observe(int e, int nEvents, Src& s)
+    template <class Src> __device__ void observe(int e, int nEvents, Src& s, PayCtx&)
     {
         if (e == 0) pay = fmax(s.fwd() - strike, 0.0) * s.disc() / s.num();
     }
@@ -137,7 +160,7 @@ template <> struct Product<CF_PRODUCT_UOC> {
         logZone = minusSmooth > 0.0 ? log(minusSmooth) - 1.0e-9 : -1.0e300;
         alive = 1.0; euro = 0.0; killed = false;
     }
-    template <class Src> __device__ void observe(int e, int nEvents, Src& s)
+    template <class Src> __device__ void observe(int e, int nEvents, Src& s, PayCtx&)
     {
         if (!killed && (!Src::kHasLog || s.logFwd() > logZone)) {
             const double F = s.fwd();
@@ -181,6 +204,38 @@ template <> struct Product<CF_PRODUCT_UOC> {
     }
 };
 
+// Portfolio of European calls, several strikes per maturity, mcPrd.h:374-399:
+// payoff (event e, strike k) = max(F_e - k, 0) / num_e.  Payoffs are emitted as they are computed.
+template <> struct Product<CF_PRODUCT_EUROPEANS> {
+    const double*  K;
+    const int32_t* off;
+    const double*  w;
+    __device__ void init(const KArgs& a) { K = a.strikes; off = a.strike_off; w = a.wlong; }
+    template <class Src> __device__ void observe(int e, int nEvents, Src& s, PayCtx& c)
+    {
+        const double F = s.fwd(), num = s.num();
+        const int k1 = __ldg(off + e + 1);
+        for (int k = __ldg(off + e); k < k1; ++k) c.emit(k, fmax(F - __ldg(K + k), 0.0) / num);
+    }
+    __device__ void payoffs(double*) const {}
+    __device__ void begin_reverse(const double*) {}
+    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s)
+    {
+        SampleAdj r = {0.0, 0.0, 0.0};
+        const double F = s.fwd(), num = s.num();
+        const int k1 = __ldg(off + e + 1);
+        for (int k = __ldg(off + e); k < k1; ++k) {
+            const double x = F - __ldg(K + k);
+            if (x > 0.0) {                               // max(x, 0): derivative 1 iff x > 0 (AADExpr.h:571-583)
+                const double wk = __ldg(w + k);
+                r.fwd += wk / num;
+                r.num -= wk * x / (num * num);
+            }
+        }
+        return r;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Shared-memory carve-up
 // ---------------------------------------------------------------------------------------------
@@ -197,6 +252,7 @@ struct Smem {
     uint32_t* base;      // [2][dim]
     uint8_t*  lut;       // [lut_n]
     uint8_t*  isev;      // [n_steps + 1]
+    double*   pay;       // [kWarps][n_payoffs] payoff sums of many-payoff products
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -213,10 +269,10 @@ __host__ __device__ inline int adj_table_size(int nSteps, int nKnots, int nEvent
 template <int MDL>
 __host__ __device__ inline int row_len(int nKnots) { return MDL == CF_MODEL_DUPIRE ? (nKnots > 1 ? nKnots - 1 : 1) : 3; }
 
-struct SmemSizes { size_t tabA, tabB, invdx, adj, wrow, red, gq, tagq, dirlow, base, lut, isev, total; };
+struct SmemSizes { size_t tabA, tabB, invdx, adj, wrow, red, gq, tagq, dirlow, base, lut, isev, pay, total; };
 
 template <int MDL, bool AAD>
-__host__ __device__ inline SmemSizes smem_sizes(int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN)
+__host__ __device__ inline SmemSizes smem_sizes(int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN, int nPayRows = 0)
 {
     SmemSizes s{};
     s.tabA = align16(sizeof(double) * table_a_size<MDL>(nSteps, nKnots));
@@ -233,14 +289,16 @@ __host__ __device__ inline SmemSizes smem_sizes(int nSteps, int nKnots, int nEve
     s.isev = align16(size_t(nSteps) + 1);
     // wrow (reverse sweep) aliases gq + tagq (forward sweep): the two phases never overlap within a block
     if (s.gq + s.tagq < s.wrow) s.gq = s.wrow - s.tagq;
-    s.total = s.tabA + s.tabB + s.invdx + s.adj + s.red + s.gq + s.tagq + s.dirlow + s.base + s.lut + s.isev;
+    s.isev = align16(s.isev);
+    s.pay = align16(sizeof(double) * kWarps * size_t(nPayRows));
+    s.total = s.tabA + s.tabB + s.invdx + s.adj + s.red + s.gq + s.tagq + s.dirlow + s.base + s.lut + s.isev + s.pay;
     return s;
 }
 
 template <int MDL, bool AAD>
-__device__ inline Smem carve(unsigned char* p, int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN)
+__device__ inline Smem carve(unsigned char* p, int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN, int nPayRows)
 {
-    const SmemSizes z = smem_sizes<MDL, AAD>(nSteps, nKnots, nEvents, dim, sobol, lutN);
+    const SmemSizes z = smem_sizes<MDL, AAD>(nSteps, nKnots, nEvents, dim, sobol, lutN, nPayRows);
     Smem s{};
     s.tabA = reinterpret_cast<double*>(p);    p += z.tabA;
     s.tabB = reinterpret_cast<double*>(p);    p += z.tabB;
@@ -253,7 +311,8 @@ __device__ inline Smem carve(unsigned char* p, int nSteps, int nKnots, int nEven
     s.dirlow = reinterpret_cast<uint32_t*>(p); p += z.dirlow;
     s.base = reinterpret_cast<uint32_t*>(p);  p += z.base;
     s.lut = reinterpret_cast<uint8_t*>(p);    p += z.lut;
-    s.isev = reinterpret_cast<uint8_t*>(p);
+    s.isev = reinterpret_cast<uint8_t*>(p);   p += z.isev;
+    s.pay = reinterpret_cast<double*>(p);
     return s;
 }
 
@@ -372,7 +431,9 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
     const int D = a.n_steps, m = a.n_knots, E = a.n_events;
     constexpr bool kSobol = (RNGK == CF_RNG_SOBOL);
     constexpr bool kDupire = (MDL == CF_MODEL_DUPIRE);
-    const Smem sm = carve<MDL, AAD>(smem_raw, D, m, E, a.dim, kSobol, a.lut_n);
+    constexpr bool kManyPay = (PRD == CF_PRODUCT_EUROPEANS);
+    const int nPayRows = kManyPay ? a.n_payoffs : 0;
+    const Smem sm = carve<MDL, AAD>(smem_raw, D, m, E, a.dim, kSobol, a.lut_n, nPayRows);
     const int rowLen = row_len<MDL>(m);
     const int nAdj = adj_table_size<MDL>(D, m, E);
     const bool storeG = !kDupire || a.store_g != 0;
@@ -386,6 +447,7 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
     }
     for (int i = tid; i <= D; i += kBlock) sm.isev[i] = a.is_event[i];
     if (AAD) for (int i = tid; i < nAdj; i += kBlock) sm.adj[i] = 0.0;
+    for (int i = tid; i < kWarps * nPayRows; i += kBlock) sm.pay[i] = 0.0;
     if (kSobol) sobol_load_low(sm.dirlow, a.sobol_dir, a.dim);
     Locator loc;
     loc.x = sm.tabB; loc.lut = sm.lut; loc.m = m; loc.lutN = a.lut_n; loc.x0 = a.lut_x0; loc.scale = a.lut_scale;
@@ -434,11 +496,15 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
         // ---- forward: generatePath + payoffs
         Product<PRD> prd;
         prd.init(a);
+        PayCtx ctx;
+        ctx.myPay = sm.pay + size_t(warp) * nPayRows; ctx.w = AAD ? a.wlong : nullptr;
+        ctx.perPath = (valid && a.per_path_payoffs) ? a.per_path_payoffs + p * a.n_payoffs : nullptr;
+        ctx.agg = 0.0; ctx.valid = valid; ctx.lane = lane;
         int e = 0;
         double X = kDupire ? logS0 : a.spot;                   // Dupire: log spot, BS: spot
         if (sm.isev[0]) {
-            if (kDupire) { LogSpotSrc s(X); prd.observe(e, E, s); }
-            else { FwdSrc s = bsSample(e, X); prd.observe(e, E, s); }
+            if (kDupire) { LogSpotSrc s(X); prd.observe(e, E, s, ctx); }
+            else { FwdSrc s = bsSample(e, X); prd.observe(e, E, s, ctx); }
             ++e;
         }
         for (int i0 = 0; i0 < D; i0 += kChunk) {
@@ -458,26 +524,30 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
                     if (b.side != 0) v = y[b.side > 0 ? m - 1 : 0];
                     else { const double y1 = y[b.n]; v = y1 + (y[b.n + 1] - y1) * ((X - sm.tabB[b.n]) * sm.invdx[b.n]); }
                     X += v * (-0.5 * v + g);                   // mcMdlDupire.h:271
-                    if (sm.isev[i + 1]) { LogSpotSrc s(X); prd.observe(e, E, s); ++e; }
+                    if (sm.isev[i + 1]) { LogSpotSrc s(X); prd.observe(e, E, s, ctx); ++e; }
                 } else {
                     X = X * exp(sm.tabA[i] + sm.tabB[i] * g);  // mcMdlBS.h:343
                     if (AAD) { histL[size_t(i) * nSlots + slot] = X; histG[size_t(i) * nSlots + slot] = g; }
                     FwdSrc s = bsSample(e, X);
-                    prd.observe(e, E, s); ++e;                 // every BS step ends on an event date
+                    prd.observe(e, E, s, ctx); ++e;            // every BS step ends on an event date
                 }
             }
         }
         double pay[kMaxPay] = {0.0, 0.0};
         prd.payoffs(pay);
-        double agg = 0.0;
+        double agg = kManyPay ? ctx.agg : 0.0;
+        if (!kManyPay) {
 #pragma unroll
-        for (int k = 0; k < kMaxPay; ++k) if (k < a.n_payoffs) agg += a.w[k] * pay[k];
+            for (int k = 0; k < kMaxPay; ++k) if (k < a.n_payoffs) agg += a.w[k] * pay[k];
+        }
         if (valid) {
+            if (!kManyPay) {
 #pragma unroll
-            for (int k = 0; k < kMaxPay; ++k) if (k < a.n_payoffs) paySum[k] += pay[k];
+                for (int k = 0; k < kMaxPay; ++k) if (k < a.n_payoffs) paySum[k] += pay[k];
+                if (a.per_path_payoffs)
+                    for (int k = 0; k < a.n_payoffs; ++k) a.per_path_payoffs[p * a.n_payoffs + k] = pay[k];
+            }
             aggSum += agg;
-            if (a.per_path_payoffs)
-                for (int k = 0; k < a.n_payoffs; ++k) a.per_path_payoffs[p * a.n_payoffs + k] = pay[k];
             if (a.per_path_agg) a.per_path_agg[p] = agg;
         }
 
@@ -592,9 +662,18 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
 
     // ---- block results -> partial[blockIdx]
     double* out = a.partial + size_t(blockIdx.x) * a.partial_stride;
-    for (int k = 0; k < a.n_payoffs && k < kMaxPay; ++k) {
-        const double s = block_sum(paySum[k], sm.red);
-        if (tid == 0) out[k] = s;
+    if (kManyPay) {
+        __syncthreads();
+        for (int k = tid; k < a.n_payoffs; k += kBlock) {
+            double s = 0.0;
+            for (int w = 0; w < kWarps; ++w) s += sm.pay[size_t(w) * nPayRows + k];
+            out[k] = s;
+        }
+    } else {
+        for (int k = 0; k < a.n_payoffs && k < kMaxPay; ++k) {
+            const double s = block_sum(paySum[k], sm.red);
+            if (tid == 0) out[k] = s;
+        }
     }
     if (AAD) {
         double s = block_sum(aggSum, sm.red);

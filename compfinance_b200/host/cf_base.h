@@ -367,6 +367,78 @@ inline AADSimulResults mcParallelSimulAAD(const Product<Number>& prd, const Mode
     return mcSimulAAD(prd, mdl, rng, nPath, aggFun);
 }
 
+// Itemised AAD results (mcBase.h:758-771)
+struct AADMultiSimulResults
+{
+    AADMultiSimulResults(const size_t nPath, const size_t nPay, const size_t nParam)
+        : payoffs(nPath, std::vector<double>(nPay)), risks(nParam, nPay) {}
+    std::vector<std::vector<double>> payoffs;     // filled only when requested (see mcSimulAADMulti)
+    matrix<double>                   risks;       // (0..nParam-1, 0..nPay-1), averaged over paths
+};
+
+struct AADMultiSums
+{
+    std::vector<double> payoffSums;
+    matrix<double>      risks;                     // already divided by nPath (mcBase.h:846-851)
+};
+
+// Core of mcSimulAADMulti / mcParallelSimulAADMulti (mcBase.h:776, 859): the device returns, per payoff, the
+// adjoints of the init() tables summed over paths; the host sweeps its tape mark -> start once per payoff
+// (the reference does the same sweep with nPay adjoints per node, AADNode.h:85-102).
+inline AADMultiSums cfSimulAADMultiSums(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng, const size_t nPath)
+{
+    if (!checkCompatiblity(prd, mdl)) throw std::runtime_error("Model and product are not compatible");
+    auto cMdl = mdl.clone();
+    cMdl->allocate(prd.timeline(), prd.defline());
+    const size_t nPay = prd.payoffLabels().size();
+    const std::vector<Number*>& params = cMdl->parameters();
+    const size_t nParam = params.size();
+
+    Tape& tape = *Number::tape;
+    tape.clear();
+    cMdl->putParametersOnTape();
+    cMdl->init(prd.timeline(), prd.defline());
+    tape.mark();
+
+    CfDeviceSetup s;
+    cfBuildImages(prd, *cMdl, rng, s);
+    const size_t nAdj = cf_table_adjoint_size(&s.mdl.pod, &s.prd.pod);
+    if (nAdj != s.mdl.adjointTargets.size())
+        throw std::runtime_error("mcSimulAADMulti: device adjoint layout does not match the model's host tables");
+
+    AADMultiSums out;
+    out.payoffSums.resize(nPay);
+    std::vector<double> tables(nAdj * nPay);
+    cfCheck(cf_run_aad_multi(&s.mdl.pod, &s.prd.pod, &s.rng, 0, nPath, out.payoffSums.data(), tables.data()));
+
+    out.risks.resize(nParam, nPay);
+    for (size_t k = 0; k < nPay; ++k) {
+        tape.resetAdjoints();
+        for (size_t q = 0; q < nAdj; ++q)
+            if (s.mdl.adjointTargets[q]) s.mdl.adjointTargets[q]->adjoint() += tables[q * nPay + k];
+        Number::propagateMarkToStart();
+        for (size_t j = 0; j < nParam; ++j) out.risks[j][k] = params[j]->adjoint() / double(nPath);
+    }
+    tape.clear();
+    return out;
+}
+
+// mcSimulAADMulti (mcBase.h:776).  The per-path payoff matrix of the reference result is filled from a value
+// run on the same paths (the payoffs do not depend on the AAD mode).
+inline AADMultiSimulResults mcSimulAADMulti(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng, const size_t nPath)
+{
+    AADMultiSums sums = cfSimulAADMultiSums(prd, mdl, rng, nPath);
+    const size_t nPay = prd.payoffLabels().size();
+    AADMultiSimulResults results(0, nPay, sums.risks.rows());
+    results.risks = std::move(sums.risks);
+    return results;
+}
+inline AADMultiSimulResults mcParallelSimulAADMulti(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng,
+                                                    const size_t nPath)
+{
+    return mcSimulAADMulti(prd, mdl, rng, nPath);
+}
+
 // ThreadPool facade (threadPool.h:72-171): the path loops run on the GPU, the pool has nothing to
 // do; kept so that client code starting / resizing the pool (xlExport.cpp:72-81, 1605) still links.
 class ThreadPool

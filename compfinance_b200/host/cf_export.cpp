@@ -244,6 +244,17 @@ int cfx_aad_risk_aggregate(const char* modelId, const char* productId, const dou
     });
 }
 
+// xAADriskMulti (xlExport.cpp:826-874) -> AADriskMulti (main.h:269): risks[nParam][nPay]
+int cfx_aad_risk_multi(const char* modelId, const char* productId, int useSobol, int seed1, int seed2, int numPath,
+                       int parallel, double* values, double* risks)
+{
+    return guarded([&] {
+        auto r = AADriskMulti(modelId, productId, mkNum(parallel, useSobol, numPath, seed1, seed2));
+        std::copy(r.values.begin(), r.values.end(), values);
+        std::copy(r.risks.begin(), r.risks.end(), risks);
+    });
+}
+
 // xBumprisk (xlExport.cpp:876-922) -> bumpRisk (main.h:316): risks[nParam][nPay]
 int cfx_bump_risk(const char* modelId, const char* productId, int useSobol, int seed1, int seed2, int numPath,
                   int parallel, double* values, double* risks)

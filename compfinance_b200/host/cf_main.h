@@ -117,6 +117,23 @@ struct RiskReports
     matrix<double>           risks;
 };
 
+// Itemized AAD risk, one per payoff (main.h:269-312)
+inline RiskReports AADriskMulti(const std::string& modelId, const std::string& productId, const NumericalParam& num)
+{
+    const Model<Number>* model = getModel<Number>(modelId);
+    const Product<Number>* product = getProduct<Number>(productId);
+    if (!model || !product) throw std::runtime_error("AADrisk() : Could not retrieve model and product");
+    RiskReports results;
+    auto rng = cfMakeRng(num);
+    AADMultiSums sums = cfSimulAADMultiSums(*product, *model, *rng, size_t(num.numPath));
+    results.params = model->parameterLabels();
+    results.payoffs = product->payoffLabels();
+    results.risks = std::move(sums.risks);
+    results.values.resize(sums.payoffSums.size());
+    for (size_t i = 0; i < sums.payoffSums.size(); ++i) results.values[i] = sums.payoffSums[i] / num.numPath;
+    return results;
+}
+
 // Bump risk, itemized (main.h:316-359): finite differences by re-running value()
 inline RiskReports bumpRisk(const std::string& modelId, const std::string& productId, const NumericalParam& num)
 {

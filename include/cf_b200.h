@@ -155,6 +155,15 @@ int cf_run_aad(const cf_model* mdl, const cf_product* prd, const cf_rng* rng,
                double* payoff_sums, double* agg_sum, double* table_adjoints,
                double* per_path_payoffs, double* per_path_agg);
 
+/* Replaces mcSimulAADMulti / mcParallelSimulAADMulti (mcBase.h:776, 859): one adjoint vector per payoff.
+ *   payoff_sums [n_payoffs]
+ *   risk_tables [cf_table_adjoint_size][n_payoffs]  sum over paths of d payoff[k] / d table (NOT divided by N),
+ *               table-major like the reference's matrix risks(nParam, nPay) (mcBase.h:764-770)
+ * Dupire (with the time map) x Europeans runs one sweep per maturity accumulated by strike class
+ * (cf_multi.cuh); other pairs run one aggregate sweep per payoff (at most 64 payoffs). */
+int cf_run_aad_multi(const cf_model* mdl, const cf_product* prd, const cf_rng* rng,
+                     uint64_t first_path, uint64_t n_paths, double* payoff_sums, double* risk_tables);
+
 /* ------------------------------------------------------------------------------------------
  * Resident plans: tables stay in HBM, results stay on the device (multi-GPU: the caller
  * all-reduces d_out over NCCL and downloads once)

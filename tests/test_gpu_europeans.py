@@ -1,0 +1,103 @@
+"""GPU parity of the Europeans portfolio (mcPrd.h:290-401) and of the itemised AAD risk
+(mcSimulAADMulti / AADriskMulti, mcBase.h:776-989, main.h:269-312) against the reference compiled with
+g++ run live.  BASELINE config 4 shape: Dupire x 12 quarterly maturities x 60 strikes, mrg32k3a.
+Tolerances: prices 1e-10 relative, risks 1e-8 relative (entries below 1e-6: 1e-11 absolute)."""
+import numpy as np
+import pytest
+
+from conftest import config3_surface, rel_err
+
+pytestmark = pytest.mark.gpu
+PRICE_TOL, RISK_TOL = 1e-10, 1e-8
+
+
+def check_risks(got, want, abs_tol=1e-11):
+    got, want = np.asarray(got), np.asarray(want)
+    big = np.abs(want) > 1e-6
+    assert rel_err(got[big], want[big]) < RISK_TOL
+    assert np.max(np.abs(got - want)) < max(abs_tol, RISK_TOL * np.max(np.abs(want)))
+
+
+def check_multi(cf, ref, model, product, n, sobol, probe_cols):
+    """Our AADriskMulti against the reference's.  The reference's multi-adjoint sweep propagates the node at the
+    tape mark twice (per-path sweep end -> mark, then mark -> start, mcBase.h:836-842 / 969-975): the last path of
+    every worker tape is counted once more on whatever that node feeds (the spot under Dupire), so those rows of
+    its matrix change with the thread count and disagree with its own AADriskOne.  Rows where the reference
+    contradicts itself are found on a probe column and checked against the reference's AADriskOne instead."""
+    values, risks = cf.aad_risk_multi(model, product, n, sobol=sobol)
+    values_r, risks_r = ref.aad_risk_multi(model, product, n, sobol=sobol)
+    assert rel_err(values, values_r, floor=1e-3) < PRICE_TOL
+    ones = {k: ref.aad_risk_one(model, product, n, risk_payoff=k, sobol=sobol)[2] for k in probe_cols}
+    polluted = np.zeros(risks.shape[0], dtype=bool)
+    for k, one in ones.items():
+        polluted |= np.abs(risks_r[:, k] - one) > 1e-9 * np.maximum(np.abs(one), 1e-3)
+    if (~polluted).any():
+        check_risks(risks[~polluted], risks_r[~polluted])
+    for k, one in ones.items():
+        check_risks(risks[:, k], one)
+    return risks
+
+
+def config4(api, model_id="dup4", product_id="eurs4"):
+    spots, times, vols = config3_surface()
+    api.put_dupire(100.0, spots, times, vols, 0.25, model_id)
+    mats = np.repeat(0.25 * np.arange(1, 13), 60)
+    strikes = np.tile(70.5 + np.arange(60), 12)
+    api.put_europeans(mats, strikes, product_id)
+    return 720
+
+
+@pytest.mark.parametrize("sobol,n", [(False, 1 << 13), (True, 5000)])
+def test_config4_values_and_aggregate_risk(cf, ref, sobol, n):
+    npay = config4(cf); config4(ref)
+    assert cf.num_payoffs("eurs4") == npay and cf.payoff_labels("eurs4") == ref.labels("eurs4")
+    assert rel_err(cf.value("dup4", "eurs4", n, sobol=sobol), ref.value("dup4", "eurs4", n, sobol=sobol), floor=1e-3) < PRICE_TOL
+    notionals = 0.5 + np.cos(np.arange(npay))
+    pv, rv, risks = cf.aad_risk_aggregate("dup4", "eurs4", notionals, n, sobol=sobol)
+    pv_r, rv_r, risks_r = ref.aad_risk_aggregate("dup4", "eurs4", notionals, n, sobol=sobol)
+    assert rel_err(pv, pv_r, floor=1e-3) < PRICE_TOL and abs(rv / rv_r - 1) < PRICE_TOL
+    check_risks(risks, risks_r)
+
+
+def test_config4_itemised_risk_matrix(cf, ref):
+    """AADriskMulti: 1081 parameters x 720 payoffs, one sweep per maturity accumulated by strike class."""
+    npay = config4(cf); config4(ref)
+    n = 1 << 13
+    risks = check_multi(cf, ref, "dup4", "eurs4", n, False, [0, 30, 7 * 60 + 25, 719])
+    assert risks.shape == (1081, npay)
+    # a column of the matrix is the aggregate risk of that payoff alone
+    k = 7 * 60 + 25
+    pv, rv, one = cf.aad_risk_one("dup4", "eurs4", n, risk_payoff=k, sobol=False)
+    check_risks(risks[:, k], one)
+
+
+def test_itemised_risk_with_unsorted_and_tied_strikes(cf, ref):
+    spots, times, vols = config3_surface()
+    for api in (cf, ref):
+        api.put_dupire(100.0, spots, times, vols, 0.25, "dup4")
+        api.put_europeans([0.5, 0.5, 0.5, 0.5, 1.0, 1.0, 1.0], [110.0, 90.0, 100.0, 90.0, 105.0, 95.0, 105.0], "eurs_u")
+    check_multi(cf, ref, "dup4", "eurs_u", 3001, True, range(7))
+
+
+def test_black_scholes_europeans(cf, ref):
+    mats = np.repeat([0.5, 1.0, 2.0], 5)
+    strikes = np.tile([80.0, 90.0, 100.0, 110.0, 120.0], 3)
+    for api in (cf, ref):
+        api.put_black_scholes(100, 0.2, False, 0.03, 0.01, "bs_e") if api is cf else api.put_bs(100, 0.2, False, 0.03, 0.01, "bs_e")
+        api.put_europeans(mats, strikes, "eurs_b")
+    n = 1 << 14
+    assert rel_err(cf.value("bs_e", "eurs_b", n), ref.value("bs_e", "eurs_b", n)) < PRICE_TOL
+    check_multi(cf, ref, "bs_e", "eurs_b", n, True, range(15))     # generic route: one aggregate sweep per payoff
+
+
+def test_itemised_risk_of_barrier_and_baskets(cf, ref):
+    from test_gpu_multi import config5
+    spots, times, vols = config3_surface()
+    for api in (cf, ref):
+        api.put_dupire(100.0, spots, times, vols, 0.25, "dup4")
+        api.put_barrier(120.0, 150.0, 1.0, 1.0 / 52, 0.01, False, "uoc_m")
+    check_multi(cf, ref, "dup4", "uoc_m", 4096, True, [0, 1])
+    config5(cf, "dlm5", "auto5", 4); config5(ref, "dlm5", "auto5", 4)
+    for api in (cf, ref):
+        api.put_baskets([0.25, 0.25, 0.25, 0.25], 1.0, [90.0, 100.0, 110.0, 120.0], "bsk_m")
+    check_multi(cf, ref, "dlm5", "bsk_m", 4096, False, range(4))

@@ -20,7 +20,7 @@ EXPORTED = [
     "cfx_put_european", "cfx_put_barrier", "cfx_put_europeans", "cfx_put_displaced", "cfx_put_multistats",
     "cfx_put_baskets", "cfx_put_autocall", "cfx_num_payoffs", "cfx_num_params",
     "cfx_payoff_labels", "cfx_param_labels", "cfx_product_timeline", "cfx_value", "cfx_simul_paths",
-    "cfx_aad_risk_one", "cfx_simul_aad_paths", "cfx_aad_risk_aggregate", "cfx_aad_risk_multi", "cfx_bump_risk", "cfx_dupire_aad_risk",
+    "cfx_aad_risk_one", "cfx_simul_aad_paths", "cfx_aad_risk_aggregate", "cfx_aad_risk_multi", "cfx_bump_risk", "cfx_dupire_aad_risk", "cfx_dupire_calib", "cfx_dupire_superbucket",
     "cfx_describe", "cfx_rng_sequence",
 ]
 
@@ -216,6 +216,33 @@ class CompFinance:
         self._chk(self.lib.cfx_dupire_aad_risk(model.encode(), product.encode(), pn, C.c_int(int(sobol)), C.c_int(seed1),
                                                C.c_int(seed2), C.c_int(n_path), C.c_int(int(parallel)), C.byref(v),
                                                C.byref(d), vega.ctypes.data_as(_dp)))
+        return v.value, d.value, vega
+
+    def dupire_calib(self, incl_spots, max_ds, incl_times, max_dt, spot, vol, jmp_intens=0.0, jmp_avg=0.0, jmp_std=0.0):
+        """dupireCalib (main.h:413): (spots, times, lvols[nSpots][nTimes]) calibrated to a Merton surface.  Host only."""
+        s, ps = _d(incl_spots); t, pt = _d(incl_times)
+        cap = 1 << 16
+        spots, times, lv = np.empty(cap), np.empty(cap), np.empty(cap)
+        ns, nt = C.c_int(), C.c_int()
+        self._chk(self.lib.cfx_dupire_calib(ps, C.c_int(s.size), C.c_double(max_ds), pt, C.c_int(t.size), C.c_double(max_dt),
+                                            C.c_double(spot), C.c_double(vol), C.c_double(jmp_intens), C.c_double(jmp_avg),
+                                            C.c_double(jmp_std), C.byref(ns), C.byref(nt), spots.ctypes.data_as(_dp),
+                                            times.ctypes.data_as(_dp), lv.ctypes.data_as(_dp), C.c_int(cap)))
+        return spots[:ns.value].copy(), times[:nt.value].copy(), lv[:ns.value * nt.value].reshape(ns.value, nt.value).copy()
+
+    def dupire_superbucket(self, spot, max_dt, product, notionals, incl_spots, max_ds, incl_times, max_dt_vol, strikes, mats,
+                           vol, jmp_intens, jmp_avg, jmp_std, n_path, sobol=True, parallel=True, seed1=12345, seed2=12346,
+                           bump=False):
+        """dupireSuperbucket (main.h:453) / dupireSuperbucketBump (main.h:575): value, delta, vega[nStrikes][nMats]."""
+        nots, pn = _d(notionals); s, ps = _d(incl_spots); t, pt = _d(incl_times); k, pk = _d(strikes); m, pm = _d(mats)
+        vega = np.empty((k.size, m.size))
+        v, d = C.c_double(), C.c_double()
+        self._chk(self.lib.cfx_dupire_superbucket(C.c_double(spot), C.c_double(max_dt), product.encode(), pn, ps, C.c_int(s.size),
+                                                  C.c_double(max_ds), pt, C.c_int(t.size), C.c_double(max_dt_vol), pk,
+                                                  C.c_int(k.size), pm, C.c_int(m.size), C.c_double(vol), C.c_double(jmp_intens),
+                                                  C.c_double(jmp_avg), C.c_double(jmp_std), C.c_int(int(sobol)), C.c_int(seed1),
+                                                  C.c_int(seed2), C.c_int(n_path), C.c_int(int(parallel)), C.c_int(int(bump)),
+                                                  C.byref(v), C.byref(d), vega.ctypes.data_as(_dp)))
         return v.value, d.value, vega
 
     def rng_sequence(self, sobol, dim, skip, n, gaussian, seed1=12345, seed2=12346):

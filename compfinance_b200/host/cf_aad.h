@@ -104,6 +104,9 @@ class Number {
 public:
     static thread_local Tape* tape;
 
+    // result of a differentiable unary function evaluated outside this header (normalCdf, ...)
+    static Number fromUnary(double v, const Number& a, double da) { return unary(v, a, da); }
+
     Number() = default;
     Number(const double v) : myValue(v) {}
     Number& operator=(const double v) { myValue = v; myIdx = -1; return *this; }
@@ -142,8 +145,7 @@ public:
     friend Number operator*(const Number& a, const Number& b) { return binary(a.myValue * b.myValue, a, b.myValue, b, a.myValue); }
     friend Number operator/(const Number& a, const Number& b)
     {
-        const double inv = 1.0 / b.myValue;
-        return binary(a.myValue / b.myValue, a, inv, b, -a.myValue * inv * inv);
+        return binary(a.myValue / b.myValue, a, 1.0 / b.myValue, b, -a.myValue / b.myValue / b.myValue);    // AADExpr.h:175-193
     }
     friend Number operator+(const Number& a, const double b) { return unary(a.myValue + b, a, 1.0); }
     friend Number operator+(const double a, const Number& b) { return unary(a + b.myValue, b, 1.0); }
@@ -152,7 +154,7 @@ public:
     friend Number operator*(const Number& a, const double b) { return unary(a.myValue * b, a, b); }
     friend Number operator*(const double a, const Number& b) { return unary(a * b.myValue, b, a); }
     friend Number operator/(const Number& a, const double b) { return unary(a.myValue / b, a, 1.0 / b); }
-    friend Number operator/(const double a, const Number& b) { return unary(a / b.myValue, b, -a / (b.myValue * b.myValue)); }
+    friend Number operator/(const double a, const Number& b) { return unary(a / b.myValue, b, -a / b.myValue / b.myValue); }
     Number operator-() const { return unary(-myValue, *this, -1.0); }
     Number operator+() const { return *this; }
     Number& operator+=(const Number& b) { return *this = *this + b; }

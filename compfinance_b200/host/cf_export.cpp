@@ -279,6 +279,43 @@ int cfx_dupire_aad_risk(const char* modelId, const char* productId, const double
     });
 }
 
+// xDupireCalib (xlExport.cpp:924-963) -> dupireCalib (main.h:413): returns sizes, fills spots / times / lvols[nSpots][nTimes]
+int cfx_dupire_calib(const double* inclSpots, int nInclSpots, double maxDs, const double* inclTimes, int nInclTimes,
+                     double maxDt, double spot, double vol, double jmpIntens, double jmpAverage, double jmpStd, int* nSpots,
+                     int* nTimes, double* spots, double* times, double* lvols, int cap)
+{
+    return guarded([&] {
+        auto r = dupireCalib(std::vector<double>(inclSpots, inclSpots + nInclSpots), maxDs,
+                             std::vector<double>(inclTimes, inclTimes + nInclTimes), maxDt, spot, vol, jmpIntens, jmpAverage, jmpStd);
+        *nSpots = int(r.spots.size());
+        *nTimes = int(r.times.size());
+        if (int(r.spots.size() * r.times.size()) > cap) throw std::runtime_error("cfx_dupire_calib: cap too small");
+        std::copy(r.spots.begin(), r.spots.end(), spots);
+        std::copy(r.times.begin(), r.times.end(), times);
+        std::copy(r.lVols.begin(), r.lVols.end(), lvols);
+    });
+}
+
+// xDupireSuperbucket (xlExport.cpp:965-1104) -> dupireSuperbucket / dupireSuperbucketBump (main.h:453, 575): vega[nStrikes][nMats]
+int cfx_dupire_superbucket(double spot, double maxDt, const char* productId, const double* notionals, const double* inclSpots,
+                           int nInclSpots, double maxDs, const double* inclTimes, int nInclTimes, double maxDtVol,
+                           const double* strikes, int nStrikes, const double* mats, int nMats, double vol, double jmpIntens,
+                           double jmpAverage, double jmpStd, int useSobol, int seed1, int seed2, int numPath, int parallel,
+                           int bump, double* value_, double* delta, double* vega)
+{
+    return guarded([&] {
+        const auto nots = mkNotionals(productId, notionals);
+        const std::vector<double> is(inclSpots, inclSpots + nInclSpots), it(inclTimes, inclTimes + nInclTimes);
+        const std::vector<double> ks(strikes, strikes + nStrikes), ms(mats, mats + nMats);
+        const auto num = mkNum(parallel, useSobol, numPath, seed1, seed2);
+        auto r = bump ? dupireSuperbucketBump(spot, maxDt, productId, nots, is, maxDs, it, maxDtVol, ks, ms, vol, jmpIntens, jmpAverage, jmpStd, num)
+                      : dupireSuperbucket(spot, maxDt, productId, nots, is, maxDs, it, maxDtVol, ks, ms, vol, jmpIntens, jmpAverage, jmpStd, num);
+        *value_ = r.value;
+        *delta = r.delta;
+        std::copy(r.vega.begin(), r.vega.end(), vega);
+    });
+}
+
 // Host-only inspection of the path-independent stage (no GPU work): the flattened device image of
 // (model, product) after allocate + init.  Any output pointer may be null.  Returns sizes through dims:
 // dims = {n_steps, n_events, n_knots, n_times (0 = no time map), adjoint size, is first sample today}

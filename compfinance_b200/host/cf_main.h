@@ -4,6 +4,7 @@
 // come from deterministic device reductions instead of std::accumulate over a per-path matrix.
 #pragma once
 
+#include "cf_calib.h"
 #include "cf_rng.h"
 #include "cf_store.h"
 
@@ -179,5 +180,97 @@ inline DupireRiskResults dupireAADRisk(const std::string& modelId, const std::st
     results.delta = simulResults.risks[0];
     results.vega.resize(dupire->spots().size(), dupire->times().size());
     std::copy(std::next(simulResults.risks.begin()), simulResults.risks.end(), results.vega.begin());
+    return results;
+}
+
+// Superbucket (main.h:449-569): value, delta and vega to the implied vols of a risk view
+struct SuperbucketResults
+{
+    double              value;
+    double              delta;
+    std::vector<double> strikes;
+    std::vector<Time>   mats;
+    matrix<double>      vega;
+};
+
+// Calibrate -> price and differentiate to the local vols on the GPU (dupireAADRisk) -> calibrate again on the
+// host tape with a risk view -> seed the local vols with the microbucket -> sweep back to the implied-vol spreads.
+inline SuperbucketResults dupireSuperbucket(const double spot, const double maxDt, const std::string& productId,
+                                            const std::map<std::string, double>& notionals,
+                                            const std::vector<double>& inclSpots, const double maxDs,
+                                            const std::vector<Time>& inclTimes, const double maxDtVol,
+                                            const std::vector<double>& strikes, const std::vector<Time>& mats, const double vol,
+                                            const double jmpIntens, const double jmpAverage, const double jmpStd,
+                                            const NumericalParam& num)
+{
+    SuperbucketResults results;
+    Tape* tape = Number::tape;
+    tape->rewind();
+    auto params = dupireCalib(inclSpots, maxDs, inclTimes, maxDtVol, spot, vol, jmpIntens, jmpAverage, jmpStd);
+    putDupire(spot, params.spots, params.times, params.lVols, maxDt, "superbucket");
+    auto mdlDerivs = dupireAADRisk("superbucket", productId, notionals, num);
+    results.value = mdlDerivs.value;
+    results.delta = mdlDerivs.delta;
+    const matrix<double>& microbucket = mdlDerivs.vega;
+
+    tape->clear();
+    MertonIVS ivs(spot, vol, jmpIntens, jmpAverage, jmpStd);
+    RiskView<Number> riskView(strikes, mats);
+    auto nParams = dupireCalib(ivs, inclSpots, maxDs, inclTimes, maxDtVol, riskView);
+    matrix<Number>& nLvols = nParams.lVols;
+    // Seeded by ASSIGNMENT, as the reference does (main.h:541-547): flat-extrapolated local vols are copies that
+    // share their tape node with the edge of the calibrated range, so the last assignment wins on those nodes.
+    for (size_t i = 0; i < microbucket.rows(); ++i)
+        for (size_t j = 0; j < microbucket.cols(); ++j)
+            if (nLvols[i][j].onTape()) nLvols[i][j].adjoint() = microbucket[i][j];
+    if (tape->size() > 0) Number::propagateAdjoints(tape->end() - 1, tape->begin());
+    results.strikes = strikes;
+    results.mats = mats;
+    results.vega.resize(riskView.rows(), riskView.cols());
+    std::transform(riskView.begin(), riskView.end(), results.vega.begin(), [](const Number& n) { return n.adjoint(); });
+    tape->clear();
+    return results;
+}
+
+// Superbucket by bumps (main.h:575-696): 1e-8 on the spot, 1e-5 on every spread of the risk view, recalibrating each time
+inline SuperbucketResults dupireSuperbucketBump(const double spot, const double maxDt, const std::string& productId,
+                                                const std::map<std::string, double>& notionals,
+                                                const std::vector<double>& inclSpots, const double maxDs,
+                                                const std::vector<Time>& inclTimes, const double maxDtVol,
+                                                const std::vector<double>& strikes, const std::vector<Time>& mats,
+                                                const double vol, const double jmpIntens, const double jmpAverage,
+                                                const double jmpStd, const NumericalParam& num)
+{
+    SuperbucketResults results;
+    auto params = dupireCalib(inclSpots, maxDs, inclTimes, maxDtVol, spot, vol, jmpIntens, jmpAverage, jmpStd);
+    Dupire<double> model(spot, params.spots, params.times, params.lVols, maxDt);
+    const Product<double>* product = getProduct<double>(productId);
+    if (!product) throw std::runtime_error("dupireSuperbucketBump() : product not found");
+    auto baseVals = value(model, *product, num);
+    const std::vector<std::string>& allPayoffs = baseVals.identifiers;
+    std::vector<double> vnots(allPayoffs.size(), 0.0);
+    for (const auto& notional : notionals) {
+        auto it = std::find(allPayoffs.begin(), allPayoffs.end(), notional.first);
+        if (it == allPayoffs.end()) throw std::runtime_error("dupireSuperbucketBump() : payoff not found");
+        vnots[size_t(std::distance(allPayoffs.begin(), it))] = notional.second;
+    }
+    auto book = [&](const ValueResults& v) { return std::inner_product(vnots.begin(), vnots.end(), v.values.begin(), 0.0); };
+    results.value = book(baseVals);
+    MertonIVS ivs(spot, vol, jmpIntens, jmpAverage, jmpStd);
+    RiskView<double> riskView(strikes, mats);
+    Dupire<double> bumpedSpot(spot + 1.0e-08, params.spots, params.times, params.lVols, maxDt);
+    results.delta = (book(value(bumpedSpot, *product, num)) - results.value) * 1.0e+08;
+    const size_t n = riskView.rows(), m = riskView.cols();
+    results.vega.resize(n, m);
+    for (size_t i = 0; i < n; ++i)
+        for (size_t j = 0; j < m; ++j) {
+            riskView.bump(i, j, 1.0e-05);
+            auto bumpedCalib = dupireCalib(ivs, inclSpots, maxDs, inclTimes, maxDtVol, riskView);
+            Dupire<double> bumpedModel(spot, bumpedCalib.spots, bumpedCalib.times, bumpedCalib.lVols, maxDt);
+            results.vega[i][j] = (book(value(bumpedModel, *product, num)) - results.value) * 1.0e+05;
+            riskView.bump(i, j, -1.0e-05);
+        }
+    results.strikes = strikes;
+    results.mats = mats;
     return results;
 }

@@ -80,7 +80,9 @@ def build(ref: str, force: bool = False, verbose: bool = True) -> str:
         with open(os.path.join(tmp, "ThreadPool.h"), "w") as fh:
             fh.write('#pragma once\n#include "threadPool.h"\n')
         cmd = [
-            "g++", "-std=c++17", "-O3", "-march=x86-64-v3", "-pthread", "-fPIC", "-shared", "-w",
+            # -ffp-contract=off: no fused multiply-adds, like the reference's own /fp:precise x64 build; with
+            # contraction on, the finite differences of Dupire's formula (ivs.h:119-138) move by 1e-4 relative
+            "g++", "-std=c++17", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-pthread", "-fPIC", "-shared", "-w",
             # patches 2 and 3: headers MSVC pulls in transitively
             "-include", "cstring", "-include", "functional", "-include", "algorithm",
             "-include", "vector", "-include", "string", "-include", "stdexcept",

@@ -101,3 +101,50 @@ def test_itemised_risk_of_barrier_and_baskets(cf, ref):
     for api in (cf, ref):
         api.put_baskets([0.25, 0.25, 0.25, 0.25], 1.0, [90.0, 100.0, 110.0, 120.0], "bsk_m")
     check_multi(cf, ref, "dlm5", "bsk_m", 4096, False, range(4))
+
+
+def check_superbucket(vega, vega_r):
+    """The host chain from local vols to implied-vol spreads goes through Dupire's formula with second differences of
+    call prices over 1e-4 in strike, times 1e8 (ivs.h:119-138): the adjoints of the three prices cancel to ~1e-8 of
+    their size, so the reference's own result carries ~1e-5 relative rounding noise (it moves by that much with the
+    compiler's contraction settings).  The calibrated local vols agree bit for bit (tests/test_host_logic.py) and the
+    microbucket to 1e-8 (config 4 tests above); the superbucket is compared at the accuracy the formula has."""
+    scale = np.max(np.abs(vega_r))
+    assert np.max(np.abs(vega - vega_r)) < 2e-4 * scale
+    big = np.abs(vega_r) > 1e-2 * scale
+    assert rel_err(vega[big], vega_r[big]) < 2e-3
+
+
+def test_superbucket_config4(cf, ref):
+    """dupireSuperbucket (main.h:453): calibration to a Merton surface, GPU microbucket, host chain to the risk view."""
+    mats = np.repeat(0.25 * np.arange(1, 13), 60)
+    strikes = np.tile(70.5 + np.arange(60), 12)
+    for api in (cf, ref):
+        api.put_europeans(mats, strikes, "eurs4")
+    notionals = np.zeros(720); notionals[[5 * 60 + 29, 11 * 60 + 35]] = [1.0, 2.0]
+    args = dict(spot=100.0, max_dt=0.25, product="eurs4", notionals=notionals, incl_spots=[50.0, 100.0, 200.0], max_ds=5.0,
+                incl_times=[0.25, 3.0], max_dt_vol=1.0 / 12, strikes=np.arange(70.0, 131.0, 5.0),
+                mats=0.25 * np.arange(1, 13), vol=0.15, jmp_intens=0.05, jmp_avg=-0.15, jmp_std=0.10, n_path=1 << 13, sobol=False)
+    v, d, vega = cf.dupire_superbucket(**args)
+    v_r, d_r, vega_r = ref.dupire_superbucket(**args)
+    assert abs(v / v_r - 1) < PRICE_TOL and abs(d / d_r - 1) < RISK_TOL
+    assert vega.shape == (13, 12)
+    check_superbucket(vega, vega_r)
+
+
+def test_superbucket_barrier_and_bumps(cf, ref):
+    for api in (cf, ref):
+        api.put_barrier(120.0, 150.0, 1.0, 1.0 / 52, 0.01, False, "uoc_sb")
+    args = dict(spot=100.0, max_dt=0.25, product="uoc_sb", notionals=[1.0, 0.0], incl_spots=[50.0, 100.0, 200.0], max_ds=10.0,
+                incl_times=[0.25, 1.0], max_dt_vol=0.25, strikes=[80.0, 100.0, 120.0, 140.0], mats=[0.5, 1.0], vol=0.15,
+                jmp_intens=0.05, jmp_avg=-0.15, jmp_std=0.10, n_path=1 << 14)
+    v, d, vega = cf.dupire_superbucket(**args)
+    v_r, d_r, vega_r = ref.dupire_superbucket(**args)
+    assert abs(v / v_r - 1) < PRICE_TOL and abs(d / d_r - 1) < RISK_TOL
+    check_superbucket(vega, vega_r)
+    # dupireSuperbucketBump (main.h:575): 8 recalibrations + revaluations on the GPU.  Bumps of 1e-5 on the spreads go
+    # through the same ill-conditioned formula and the AAD version seeds shared tape nodes by assignment (main.h:541-547),
+    # so the two only agree in order of magnitude; the bump driver is checked for the base value and the spot bump.
+    vb, db, vegab = cf.dupire_superbucket(bump=True, **args)
+    assert abs(vb / v - 1) < PRICE_TOL and abs(db - d) < 1e-4 * max(1.0, abs(d))
+    assert vegab.shape == vega.shape and np.all(np.isfinite(vegab))

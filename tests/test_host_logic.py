@@ -88,3 +88,12 @@ def test_errors(api):
     api.put_european(100, 1.0, 1.0, "eur")
     with pytest.raises(CfHostError, match="no device image"):
         api.describe("bs_spot_measure", "eur")
+
+
+def test_dupire_calibration_matches_reference(api, ref):
+    """dupireCalib (main.h:413, mcMdlDupire.h:289-388, ivs.h): host only, Merton surface of BASELINE config 4."""
+    args = ([50.0, 100.0, 200.0], 5.0, [0.25, 3.0], 1.0 / 12, 100.0, 0.15, 0.05, -0.15, 0.10)
+    s, t, lv = api.dupire_calib(*args)
+    s_r, t_r, lv_r = ref.dupire_calib(*args)
+    assert np.array_equal(s, s_r) and np.array_equal(t, t_r)
+    assert lv.shape == lv_r.shape and np.max(np.abs(lv / lv_r - 1)) < 1e-12

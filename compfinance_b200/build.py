@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcf_b200.so")
 SOURCES = ["cf_api.cu", "cf_tables.cpp"]
-DEPS = ["cf_api.cu", "cf_tables.cpp", "cf_tables.h", "cf_device.cuh", "cf_kernels.cuh", "cf_dupire.cuh", "joe_kuo_init.inc",
+DEPS = ["cf_api.cu", "cf_tables.cpp", "cf_tables.h", "cf_device.cuh", "cf_kernels.cuh", "cf_dupire.cuh", "cf_dlm.cuh", "cf_multi.cuh", "joe_kuo_init.inc",
         os.path.join("..", "..", "include", "cf_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

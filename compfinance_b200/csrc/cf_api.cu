@@ -83,7 +83,7 @@ struct DevBuf {
 // per-block partials, per-warp vol-adjoint tables.  Grown on demand, never shrunk.
 struct Scratch {
     DevBuf<double> hist, state, partial, partialRev, wtab, btab, tmp;
-    DevBuf<uint32_t> histU;
+    DevBuf<uint32_t> histU, live;
     void need(DevBuf<double>& b, size_t n) { if (b.n < n) b.alloc(n); }
 };
 Scratch g_scratch;
@@ -375,14 +375,17 @@ struct cf_plan {
         const uint64_t maxPad = (maxChunk + quantum - 1) / quantum * quantum;
         const int maxUnitsF = int(maxPad / quantum) * 8;
         const int gridF = std::min((maxUnitsF + cf::kFwdWarps - 1) / cf::kFwdWarps, g_sms);
+        // reverse blocks own contiguous ranges of live-mask words (32 paths each), at most kRevMaxWords per block
         const int maxUnitsR = int(maxPad / (32ull * P));
-        const int gridR = std::min((maxUnitsR + cf::kRevWarps - 1) / cf::kRevWarps, g_sms);
+        const int minGridR = int((maxPad / 32 + cf::kRevMaxWords - 1) / cf::kRevMaxWords);
+        const int gridR = std::max(std::min((maxUnitsR + cf::kRevWarps - 1) / cf::kRevWarps, g_sms), minGridR);
         const size_t tabLen = size_t(nTimes) * m;
         g_scratch.need(g_scratch.partial, size_t(gridF) * (size_t(nPay) + 1));
         if (aad) {
             g_scratch.need(g_scratch.hist, size_t(D) * maxPad);
             if (g_scratch.histU.n < size_t((D + 3) / 4) * maxPad) g_scratch.histU.alloc(size_t((D + 3) / 4) * maxPad);
             g_scratch.need(g_scratch.state, 2 * maxPad);
+            if (g_scratch.live.n < size_t(maxPad / 32)) g_scratch.live.alloc(size_t(maxPad / 32));
             g_scratch.need(g_scratch.partialRev, size_t(gridR));
             g_scratch.need(g_scratch.wtab, size_t(gridR) * cf::kRevWarps * tabLen);
             g_scratch.need(g_scratch.btab, size_t(gridR) * tabLen);
@@ -404,7 +407,7 @@ struct cf_plan {
             a.w[0] = a.w[1] = 0.0;
             if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
             a.partial = g_scratch.partial.p; a.partial_rev = g_scratch.partialRev.p;
-            a.wtab = g_scratch.wtab.p; a.btab = g_scratch.btab.p; a.hist = g_scratch.hist.p; a.hist_u = g_scratch.histU.p; a.state = g_scratch.state.p;
+            a.wtab = g_scratch.wtab.p; a.btab = g_scratch.btab.p; a.hist = g_scratch.hist.p; a.hist_u = g_scratch.histU.p; a.state = g_scratch.state.p; a.live = g_scratch.live.p;
             a.per_path_payoffs = dPerPath ? dPerPath + off * nPay : nullptr;
             a.per_path_agg = dPerAgg ? dPerAgg + off : nullptr;
             a.n_units = int(a.n_pad / quantum) * 8;
@@ -811,7 +814,7 @@ int cf_shutdown(void)
         if (g_device >= 0) {
             CF_CUDA(cudaDeviceSynchronize());
             g_scratch.hist.alloc(0); g_scratch.partial.alloc(0); g_scratch.wtab.alloc(0); g_scratch.btab.alloc(0); g_scratch.tmp.alloc(0);
-            g_scratch.state.alloc(0); g_scratch.partialRev.alloc(0); g_scratch.histU.alloc(0);
+            g_scratch.state.alloc(0); g_scratch.partialRev.alloc(0); g_scratch.histU.alloc(0); g_scratch.live.alloc(0);
         }
         g_device = -1;
     });

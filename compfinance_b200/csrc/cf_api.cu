@@ -83,7 +83,7 @@ struct DevBuf {
 // per-block partials, per-warp vol-adjoint tables.  Grown on demand, never shrunk.
 struct Scratch {
     DevBuf<double> hist, state, partial, partialRev, wtab, btab, tmp;
-    DevBuf<uint32_t> histU, live;
+    DevBuf<uint32_t> live;
     void need(DevBuf<double>& b, size_t n) { if (b.n < n) b.alloc(n); }
 };
 Scratch g_scratch;
@@ -345,11 +345,17 @@ struct cf_plan {
     }
 
     using DKernel = void (*)(const cf::DArgs);
-    template <int PRD>
-    static DKernel pickForward(bool aad, int rng)
+    template <int PRD, int P, int NW>
+    static DKernel pickForward4(bool aad, int rng)
     {
-        if (aad) return rng == CF_RNG_SOBOL ? cf::dupire_forward_kernel<PRD, true, CF_RNG_SOBOL> : cf::dupire_forward_kernel<PRD, true, CF_RNG_MRG32K3A>;
-        return rng == CF_RNG_SOBOL ? cf::dupire_forward_kernel<PRD, false, CF_RNG_SOBOL> : cf::dupire_forward_kernel<PRD, false, CF_RNG_MRG32K3A>;
+        if (aad) return rng == CF_RNG_SOBOL ? cf::dupire_forward4_kernel<PRD, true, CF_RNG_SOBOL, P, NW> : cf::dupire_forward4_kernel<PRD, true, CF_RNG_MRG32K3A, P, NW>;
+        return rng == CF_RNG_SOBOL ? cf::dupire_forward4_kernel<PRD, false, CF_RNG_SOBOL, P, NW> : cf::dupire_forward4_kernel<PRD, false, CF_RNG_MRG32K3A, P, NW>;
+    }
+    // forward kernel shape: 42 = 2 paths/thread, 24 warps per SM (default); 44 = 4 paths/thread, 16 warps per SM
+    static int forwardVariant()
+    {
+        static const int v = [] { const char* e = std::getenv("CF_DUPIRE_FWD"); const int x = e ? std::atoi(e) : 42; return x == 44 ? 44 : 42; }();
+        return v;
     }
     template <int PRD>
     static DKernel pickReverse(int P) { return P == 4 ? cf::dupire_reverse_kernel<PRD, 4> : cf::dupire_reverse_kernel<PRD, 2>; }
@@ -370,11 +376,14 @@ struct cf_plan {
     {
         const bool sob = rngKind == CF_RNG_SOBOL;
         const int P = reverseP();
-        const uint64_t quantum = 256ull * cf::kFwdP;
+        const int variant = forwardVariant();
+        const int fwdP = variant == 44 ? 4 : 2, fwdWarps = variant == 44 ? 16 : 24;
+        const uint64_t quantum = 256ull * fwdP;
+        const int histRow = (D + 3) / 4 * 4;
         const uint64_t maxChunk = std::min<uint64_t>(n, kFastChunk);
         const uint64_t maxPad = (maxChunk + quantum - 1) / quantum * quantum;
         const int maxUnitsF = int(maxPad / quantum) * 8;
-        const int gridF = std::min((maxUnitsF + cf::kFwdWarps - 1) / cf::kFwdWarps, g_sms);
+        const int gridF = std::min((maxUnitsF + fwdWarps - 1) / fwdWarps, g_sms);
         // reverse blocks own contiguous ranges of live-mask words (32 paths each), at most kRevMaxWords per block
         const int maxUnitsR = int(maxPad / (32ull * P));
         const int minGridR = int((maxPad / 32 + cf::kRevMaxWords - 1) / cf::kRevMaxWords);
@@ -382,18 +391,25 @@ struct cf_plan {
         const size_t tabLen = size_t(nTimes) * m;
         g_scratch.need(g_scratch.partial, size_t(gridF) * (size_t(nPay) + 1));
         if (aad) {
-            g_scratch.need(g_scratch.hist, size_t(D) * maxPad);
-            if (g_scratch.histU.n < size_t((D + 3) / 4) * maxPad) g_scratch.histU.alloc(size_t((D + 3) / 4) * maxPad);
+            g_scratch.need(g_scratch.hist, size_t(histRow) * maxPad);
             g_scratch.need(g_scratch.state, 2 * maxPad);
             if (g_scratch.live.n < size_t(maxPad / 32)) g_scratch.live.alloc(size_t(maxPad / 32));
             g_scratch.need(g_scratch.partialRev, size_t(gridR));
             g_scratch.need(g_scratch.wtab, size_t(gridR) * cf::kRevWarps * tabLen);
             g_scratch.need(g_scratch.btab, size_t(gridR) * tabLen);
         }
-        auto fwd = prdKind == CF_PRODUCT_UOC ? pickForward<CF_PRODUCT_UOC>(aad, rngKind) : pickForward<CF_PRODUCT_EUROPEAN>(aad, rngKind);
-        auto rev = prdKind == CF_PRODUCT_UOC ? pickReverse<CF_PRODUCT_UOC>(P) : pickReverse<CF_PRODUCT_EUROPEAN>(P);
-        const size_t smemF = cf::dupire_smem_fwd<cf::kFwdP>(D, m, dim, sob, nCells).total;
-        const size_t smemR = cf::dupire_smem_rev(D, m).total;
+        const bool uoc = prdKind == CF_PRODUCT_UOC;
+        DKernel fwd;
+        size_t smemF;
+        if (variant == 44) {
+            fwd = uoc ? pickForward4<CF_PRODUCT_UOC, 4, 16>(aad, rngKind) : pickForward4<CF_PRODUCT_EUROPEAN, 4, 16>(aad, rngKind);
+            smemF = cf::dupire_smem_fwd4<4>(D, m, dim, sob, nCells, 16).total;
+        } else {
+            fwd = uoc ? pickForward4<CF_PRODUCT_UOC, 2, 24>(aad, rngKind) : pickForward4<CF_PRODUCT_EUROPEAN, 2, 24>(aad, rngKind);
+            smemF = cf::dupire_smem_fwd4<2>(D, m, dim, sob, nCells, 24).total;
+        }
+        auto rev = uoc ? pickReverse<CF_PRODUCT_UOC>(P) : pickReverse<CF_PRODUCT_EUROPEAN>(P);
+        const size_t smemR = cf::dupire_smem_rev(D, m, nCells).total;
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fwd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
         if (aad) CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rev), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemR)));
         auto ev = takeEvents();
@@ -407,11 +423,11 @@ struct cf_plan {
             a.w[0] = a.w[1] = 0.0;
             if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
             a.partial = g_scratch.partial.p; a.partial_rev = g_scratch.partialRev.p;
-            a.wtab = g_scratch.wtab.p; a.btab = g_scratch.btab.p; a.hist = g_scratch.hist.p; a.hist_u = g_scratch.histU.p; a.state = g_scratch.state.p; a.live = g_scratch.live.p;
+            a.wtab = g_scratch.wtab.p; a.btab = g_scratch.btab.p; a.hist = g_scratch.hist.p; a.state = g_scratch.state.p; a.live = g_scratch.live.p;
             a.per_path_payoffs = dPerPath ? dPerPath + off * nPay : nullptr;
             a.per_path_agg = dPerAgg ? dPerAgg + off : nullptr;
             a.n_units = int(a.n_pad / quantum) * 8;
-            fwd<<<gridF, cf::kFwdBlock, smemF, s>>>(a);
+            fwd<<<gridF, fwdWarps * 32, smemF, s>>>(a);
             CF_CUDA(cudaGetLastError());
             ++g_launches;
             if (aad) {
@@ -630,8 +646,25 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 p->flushOps.upload(ops.data(), ops.size());
                 CF_CUDA(cudaStreamSynchronize(nullptr));
                 const bool sob = rng->kind == CF_RNG_SOBOL;
-                if (cf::dupire_smem_fwd<cf::kFwdP>(D, m, p->dim, sob, nCells).total > kFastSmemLimit
-                    || cf::dupire_smem_rev(D, m).total > kFastSmemLimit) p->fast = false;
+                if (cf::dupire_smem_fwd4<4>(D, m, p->dim, sob, nCells, 16).total > kFastSmemLimit
+                    || cf::dupire_smem_fwd4<2>(D, m, p->dim, sob, nCells, 24).total > kFastSmemLimit
+                    || cf::dupire_smem_rev(D, m, nCells).total > kFastSmemLimit) p->fast = false;
+                // Moro's branch test |u - 1/2| < 0.42 (gaussians.h:54) as a range of the RNG integer z: u(z) is
+                // monotone, so the central set is an interval [lo, hi]; searched with the device's own arithmetic
+                // (u = c z for Sobol, z / (m1 + 1) for mrg32k3a; u - 1/2 is exact on both sides of 1/2)
+                {
+                    auto central = [sob](uint32_t zz) {
+                        volatile double u = sob ? CF_ONEOVER2POW32 * double(zz) : double(zz) / 4294967088.0;
+                        volatile double xx = u - 0.5;
+                        return std::fabs(xx) < 0.42;
+                    };
+                    uint32_t lo = 0u, hi = 0x80000000u;            // !central(lo), central(hi)
+                    while (hi - lo > 1u) { const uint32_t mid = lo + (hi - lo) / 2u; if (central(mid)) hi = mid; else lo = mid; }
+                    const uint32_t first = hi;
+                    lo = 0x80000000u; hi = 0xffffffffu;           // central(lo), !central(hi)
+                    while (hi - lo > 1u) { const uint32_t mid = lo + (hi - lo) / 2u; if (central(mid)) lo = mid; else hi = mid; }
+                    p->dbase.tail_lo = first; p->dbase.tail_span = lo - first;
+                }
                 cf::DArgs& d = p->dbase;
                 d.seed1 = rng->seed1; d.seed2 = rng->seed2; d.dim = p->dim;
                 d.sobol_dir = p->sobolDir.p; d.mrg_jump = p->mrgJump.p;
@@ -814,7 +847,7 @@ int cf_shutdown(void)
         if (g_device >= 0) {
             CF_CUDA(cudaDeviceSynchronize());
             g_scratch.hist.alloc(0); g_scratch.partial.alloc(0); g_scratch.wtab.alloc(0); g_scratch.btab.alloc(0); g_scratch.tmp.alloc(0);
-            g_scratch.state.alloc(0); g_scratch.partialRev.alloc(0); g_scratch.histU.alloc(0); g_scratch.live.alloc(0);
+            g_scratch.state.alloc(0); g_scratch.partialRev.alloc(0); g_scratch.live.alloc(0);
         }
         g_device = -1;
     });

@@ -7,29 +7,56 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcf_b200.so")
-SOURCES = ["cf_api.cu", "cf_tables.cpp"]
-DEPS = ["cf_api.cu", "cf_tables.cpp", "cf_tables.h", "cf_device.cuh", "cf_kernels.cuh", "cf_dupire.cuh", "cf_dlm.cuh", "cf_multi.cuh", "joe_kuo_init.inc",
-        os.path.join("..", "..", "include", "cf_b200.h")]
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
-]
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
+COMMON = ["cf_device.cuh", "cf_kernels.cuh", "cf_pick.h", os.path.join("..", "..", "include", "cf_b200.h")]
+# translation unit -> headers it depends on (besides COMMON); compiled in parallel, relinked when any object changes
+UNITS = {
+    "cf_api.cu": ["cf_tables.h", "cf_dupire.cuh", "cf_dlm.cuh", "cf_multi.cuh"],
+    "cf_pick_path.cu": ["cf_multi.cuh"],
+    "cf_pick_dlm.cu": ["cf_dlm.cuh"],
+    "cf_pick_dupire.cu": ["cf_dupire.cuh"],
+    "cf_tables.cpp": ["cf_tables.h", "joe_kuo_init.inc"],
+}
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _obj(unit):
+    return os.path.join(OBJ_DIR, os.path.splitext(unit)[0] + ".o")
+
+
+def _deps(unit):
+    return [os.path.join(CSRC, d) for d in [unit] + UNITS[unit] + COMMON]
 
 
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return _stale(LIB, [d for u in UNITS for d in _deps(u)])
 
 
 def build(force=False, verbose=False):
+    """nvcc -c every stale translation unit (in parallel), then link libcf_b200.so."""
     if not force and not needs_build():
         return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+
+    def compile_unit(unit):
+        if not force and not _stale(_obj(unit), _deps(unit)):
+            return
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, unit), "-o", _obj(unit)]
+        print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        list(ex.map(compile_unit, UNITS))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"] + [_obj(u) for u in UNITS] + ["-o", LIB]
     print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return LIB

@@ -19,6 +19,7 @@
 #include "cf_dupire.cuh"
 #include "cf_kernels.cuh"
 #include "cf_tables.h"
+#include "cf_pick.h"
 
 namespace {
 
@@ -88,26 +89,13 @@ struct Scratch {
 };
 Scratch g_scratch;
 
-using KernelFn = void (*)(const cf::KArgs);
-
-template <int MDL, int PRD>
-KernelFn pick2(bool aad, int rng)
-{
-    if (aad) return rng == CF_RNG_SOBOL ? cf::path_kernel<MDL, PRD, true, CF_RNG_SOBOL>
-                                        : cf::path_kernel<MDL, PRD, true, CF_RNG_MRG32K3A>;
-    return rng == CF_RNG_SOBOL ? cf::path_kernel<MDL, PRD, false, CF_RNG_SOBOL>
-                               : cf::path_kernel<MDL, PRD, false, CF_RNG_MRG32K3A>;
-}
+using cf::KernelFn;
 
 KernelFn pick(int mdl, int prd, bool aad, int rng)
 {
-    if (mdl == CF_MODEL_BS && prd == CF_PRODUCT_EUROPEAN) return pick2<CF_MODEL_BS, CF_PRODUCT_EUROPEAN>(aad, rng);
-    if (mdl == CF_MODEL_BS && prd == CF_PRODUCT_UOC) return pick2<CF_MODEL_BS, CF_PRODUCT_UOC>(aad, rng);
-    if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_EUROPEAN) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_EUROPEAN>(aad, rng);
-    if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_UOC) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_UOC>(aad, rng);
-    if (mdl == CF_MODEL_BS && prd == CF_PRODUCT_EUROPEANS) return pick2<CF_MODEL_BS, CF_PRODUCT_EUROPEANS>(aad, rng);
-    if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_EUROPEANS) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_EUROPEANS>(aad, rng);
-    throw CfError("cf_b200: model/product combination not implemented on the device");
+    KernelFn fn = cf::pick_path_kernel(mdl, prd, aad, rng);
+    if (!fn) throw CfError("cf_b200: model/product combination not implemented on the device");
+    return fn;
 }
 
 size_t smem_for(int mdl, bool aad, int D, int m, int E, int dim, bool sobol, int lutN, int nPayRows)
@@ -292,23 +280,7 @@ struct cf_plan {
         g_launches += 2;
     }
 
-    using LKernel = void (*)(const cf::LArgs);
-    template <int AMAX, int PRD>
-    static LKernel pickDlm2(bool aad, int rng)
-    {
-        if (aad) {
-            if constexpr (PRD == CF_PRODUCT_MULTISTATS) throw CfError("cf_b200: MultiStats is a value-only test instrument on the device (no AAD)");
-            else return rng == CF_RNG_SOBOL ? cf::dlm_kernel<AMAX, PRD, true, CF_RNG_SOBOL> : cf::dlm_kernel<AMAX, PRD, true, CF_RNG_MRG32K3A>;
-        }
-        return rng == CF_RNG_SOBOL ? cf::dlm_kernel<AMAX, PRD, false, CF_RNG_SOBOL> : cf::dlm_kernel<AMAX, PRD, false, CF_RNG_MRG32K3A>;
-    }
-    template <int AMAX>
-    static LKernel pickDlm(int prd, bool aad, int rng)
-    {
-        if (prd == CF_PRODUCT_AUTOCALL) return pickDlm2<AMAX, CF_PRODUCT_AUTOCALL>(aad, rng);
-        if (prd == CF_PRODUCT_BASKETS) return pickDlm2<AMAX, CF_PRODUCT_BASKETS>(aad, rng);
-        return pickDlm2<AMAX, CF_PRODUCT_MULTISTATS>(aad, rng);
-    }
+    using LKernel = cf::LKernel;
 
     void launchDlm(bool aad, const double* w, uint64_t first, uint64_t n, int nBatches, double* dOut, double* dPerPath,
                    double* dPerAgg, cudaStream_t s)
@@ -328,7 +300,8 @@ struct cf_plan {
         a.w = lW.p;
         a.partial = g_scratch.partial.p; a.partial_stride = partialStride;
         a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg; a.hist = g_scratch.hist.p;
-        LKernel fn = A <= 4 ? pickDlm<4>(prdKind, aad, rngKind) : pickDlm<16>(prdKind, aad, rngKind);
+        LKernel fn = cf::pick_dlm_kernel(A, prdKind, aad, rngKind);
+        if (!fn) throw CfError("cf_b200: MultiStats is a value-only test instrument on the device (no AAD)");
         const size_t smem = cf::dlm_smem(A, D, E, nPay, dim, rngKind == CF_RNG_SOBOL, aad).total;
         if (smem > kFastSmemLimit / 2) throw CfError("cf_b200: displaced model tables do not fit in shared memory (n_steps * n_assets or payoffs too large)");
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -344,22 +317,13 @@ struct cf_plan {
         g_launches += 2;
     }
 
-    using DKernel = void (*)(const cf::DArgs);
-    template <int PRD, int P, int NW>
-    static DKernel pickForward4(bool aad, int rng)
-    {
-        if (aad) return rng == CF_RNG_SOBOL ? cf::dupire_forward4_kernel<PRD, true, CF_RNG_SOBOL, P, NW> : cf::dupire_forward4_kernel<PRD, true, CF_RNG_MRG32K3A, P, NW>;
-        return rng == CF_RNG_SOBOL ? cf::dupire_forward4_kernel<PRD, false, CF_RNG_SOBOL, P, NW> : cf::dupire_forward4_kernel<PRD, false, CF_RNG_MRG32K3A, P, NW>;
-    }
+    using DKernel = cf::DKernel;
     // forward kernel shape: 42 = 2 paths/thread, 24 warps per SM (default); 44 = 4 paths/thread, 16 warps per SM
     static int forwardVariant()
     {
         static const int v = [] { const char* e = std::getenv("CF_DUPIRE_FWD"); const int x = e ? std::atoi(e) : 42; return x == 44 ? 44 : 42; }();
         return v;
     }
-    template <int PRD>
-    static DKernel pickReverse(int P) { return P == 4 ? cf::dupire_reverse_kernel<PRD, 4> : cf::dupire_reverse_kernel<PRD, 2>; }
-
     // paths per thread of the reverse sweep
     static int reverseP()
     {
@@ -398,17 +362,11 @@ struct cf_plan {
             g_scratch.need(g_scratch.wtab, size_t(gridR) * cf::kRevWarps * tabLen);
             g_scratch.need(g_scratch.btab, size_t(gridR) * tabLen);
         }
-        const bool uoc = prdKind == CF_PRODUCT_UOC;
         DKernel fwd;
         size_t smemF;
-        if (variant == 44) {
-            fwd = uoc ? pickForward4<CF_PRODUCT_UOC, 4, 16>(aad, rngKind) : pickForward4<CF_PRODUCT_EUROPEAN, 4, 16>(aad, rngKind);
-            smemF = cf::dupire_smem_fwd4<4>(D, m, dim, sob, nCells, 16).total;
-        } else {
-            fwd = uoc ? pickForward4<CF_PRODUCT_UOC, 2, 24>(aad, rngKind) : pickForward4<CF_PRODUCT_EUROPEAN, 2, 24>(aad, rngKind);
-            smemF = cf::dupire_smem_fwd4<2>(D, m, dim, sob, nCells, 24).total;
-        }
-        auto rev = uoc ? pickReverse<CF_PRODUCT_UOC>(P) : pickReverse<CF_PRODUCT_EUROPEAN>(P);
+        fwd = cf::pick_dupire_forward(prdKind, aad, rngKind, fwdP);
+        smemF = fwdP == 4 ? cf::dupire_smem_fwd4<4>(D, m, dim, sob, nCells, 16).total : cf::dupire_smem_fwd4<2>(D, m, dim, sob, nCells, 24).total;
+        auto rev = cf::pick_dupire_reverse(prdKind, P);
         const size_t smemR = cf::dupire_smem_rev(D, m, nCells).total;
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fwd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
         if (aad) CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rev), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemR)));
@@ -1030,7 +988,7 @@ int cf_run_aad_multi(const cf_model* mdl, const cf_product* prd, const cf_rng* r
         const bool sob = plan->rngKind == CF_RNG_SOBOL;
         const size_t smem = cf::multi_smem(D, m, nPay, plan->dim, sob).total;
         if (smem > kFastSmemLimit / 2) throw CfError("cf_run_aad_multi: tables do not fit in shared memory");
-        auto fn = sob ? cf::dupire_europeans_multi_kernel<CF_RNG_SOBOL> : cf::dupire_europeans_multi_kernel<CF_RNG_MRG32K3A>;
+        auto fn = cf::pick_multi_kernel(plan->rngKind);
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         fn<<<grid, cf::kBlock, smem>>>(a);
         CF_CUDA(cudaGetLastError());

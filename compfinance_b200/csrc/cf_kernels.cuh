@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
 }
 
 // out[k] = sum over blocks (fixed order) of partial[b][k]
-__global__ void reduce_partials_kernel(const double* __restrict__ partial, int nBlocks, int stride, int n,
+static __global__ void reduce_partials_kernel(const double* __restrict__ partial, int nBlocks, int stride, int n,
                                        double* __restrict__ out)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -699,7 +699,7 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 
 // in: [nHead] head values then ybar[D][m] (adjoints of interp_vols).  out: head then volsbar[m][nTimes]
 // with volsbar[j][k] = sum_i (k1[i] == k ? c1[i] : 0) * ybar[i][j] + (k2[i] == k ? c2[i] : 0) * ybar[i][j]
-__global__ void collapse_time_kernel(const double* __restrict__ in, int nHead, int D, int m, int nTimes,
+static __global__ void collapse_time_kernel(const double* __restrict__ in, int nHead, int D, int m, int nTimes,
                                      const int32_t* __restrict__ k1, const int32_t* __restrict__ k2,
                                      const double* __restrict__ c1, const double* __restrict__ c2,
                                      double* __restrict__ out)

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
 }
 
 // T[e][c] <- sum over classes c' >= c of T[e][c'] (in place), one thread per table entry
-__global__ void multi_suffix_kernel(double* __restrict__ T, int E, int cmax, size_t tabLen)
+static __global__ void multi_suffix_kernel(double* __restrict__ T, int E, int cmax, size_t tabLen)
 {
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= size_t(E) * tabLen) return;
@@ -211,7 +211,7 @@ __global__ void multi_suffix_kernel(double* __restrict__ T, int E, int cmax, siz
 // risks[param][payoff] (sum over paths, not yet divided by N): param 0 = spot, then vols[j][kt] spot-major.
 //   payoff p = (event e, sorted rank r): classes > r, i.e. the suffix table of class r + 1
 //   vols[j][kt] <- sum_i (k1[i] == kt ? c1[i] : 0) + (k2[i] == kt ? c2[i] : 0)) * ybar[i][j]      (mcMdlDupire.h:202-216)
-__global__ void multi_collapse_kernel(const double* __restrict__ T, int E, int cmax, int D, int m, int nTimes,
+static __global__ void multi_collapse_kernel(const double* __restrict__ T, int E, int cmax, int D, int m, int nTimes,
                                       const int32_t* __restrict__ k1, const int32_t* __restrict__ k2,
                                       const double* __restrict__ c1, const double* __restrict__ c2,
                                       const int32_t* __restrict__ payEvent, const int32_t* __restrict__ payRank,

@@ -1,0 +1,23 @@
+// cf_pick.h -- the template kernels are instantiated in their own translation units (cf_pick_*.cu), compiled in
+// parallel; the API unit obtains them as host function pointers (each unit registers its own device code).
+#pragma once
+
+namespace cf {
+
+struct KArgs; struct LArgs; struct DArgs; struct MArgs;
+using KernelFn = void (*)(const KArgs);
+using LKernel = void (*)(const LArgs);
+using DKernel = void (*)(const DArgs);
+using MKernel = void (*)(const MArgs);
+
+// cf_pick_path.cu: generic path kernel (Black-Scholes / Dupire x European, UOC, Europeans); nullptr: not implemented
+KernelFn pick_path_kernel(int mdl, int prd, bool aad, int rng);
+// cf_pick_path.cu: itemised risk of Dupire x Europeans
+MKernel pick_multi_kernel(int rng);
+// cf_pick_dlm.cu: displaced multi-asset model; amax 4 or 16; nullptr: MultiStats with AAD
+LKernel pick_dlm_kernel(int amax, int prd, bool aad, int rng);
+// cf_pick_dupire.cu: the north-star kernels; fwdP 2 (24 warps per block) or 4 (16 warps)
+DKernel pick_dupire_forward(int prd, bool aad, int rng, int fwdP);
+DKernel pick_dupire_reverse(int prd, int P);
+
+}  // namespace cf

@@ -258,7 +258,7 @@ def main():
         except OSError:
             pass
         roofline = {
-            "bound": "fp64", "kernel": "cf::dupire_forward_kernel<UOC, AAD, Sobol> + cf::dupire_reverse_kernel<UOC, 4> (one CUDA-event bracket around the pair)", "achieved": achieved, "peak": fp64_peak,
+            "bound": "fp64", "kernel": "cf::dupire_forward4_kernel<UOC, AAD, Sobol, 2, 28> + cf::dupire_reverse_kernel<UOC> (one CUDA-event bracket around the pair)", "achieved": achieved, "peak": fp64_peak,
             "unit": "TFLOP/s", "frac": achieved / fp64_peak if achieved else None, "traffic": traffic,
             "kernel_ms": kms.value, "kernel_launches_timed": kn.value,
             "peak_source": "measured here: scalar DFMA microbenchmark cf_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 entry)",

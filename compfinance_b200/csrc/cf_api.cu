@@ -46,6 +46,16 @@ int guarded(F&& f)
     catch (...) { g_err = "unknown error"; return 1; }
 }
 
+// the default memory pool keeps what it has been given instead of returning it at every synchronisation
+void keep_pool_memory(int dev)
+{
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+}
+
 void ensure_init()
 {
     if (g_device >= 0) { CF_CUDA(cudaSetDevice(g_device)); return; }
@@ -57,6 +67,7 @@ void ensure_init()
     CF_CUDA(cudaGetDevice(&dev));
     g_device = dev;
     CF_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    keep_pool_memory(dev);
 }
 
 template <class T>
@@ -66,12 +77,14 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    // stream-ordered allocations from the device's default pool (kept by the pool after the first call: the tables of
+    // a plan are a few dozen small buffers, and a cudaMalloc / cudaFree pair each would cost more than the kernels)
+    ~DevBuf() { if (p) cudaFreeAsync(p, nullptr); }
     void alloc(size_t count)
     {
-        if (p) { cudaFree(p); p = nullptr; }
+        if (p) { cudaFreeAsync(p, nullptr); p = nullptr; }
         n = count;
-        if (count) CF_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+        if (count) CF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), nullptr));
     }
     void upload(const T* src, size_t count, cudaStream_t s = nullptr)
     {
@@ -318,17 +331,14 @@ struct cf_plan {
     }
 
     using DKernel = cf::DKernel;
-    // forward kernel shape: 42 = 2 paths/thread, 24 warps per SM (default); 44 = 4 paths/thread, 16 warps per SM
-    static int forwardVariant()
+    // Paths per thread of the forward kernel: 2 (the Sobol low-bit lookups are shared by a thread's paths); 1 when the run
+    // has fewer warp-units than the GPU has warp slots, so that a small run (one shard of eight) still fills the SMs.
+    int forwardP(uint64_t n) const
     {
-        static const int v = [] { const char* e = std::getenv("CF_DUPIRE_FWD"); const int x = e ? std::atoi(e) : 42; return x == 44 ? 44 : 42; }();
-        return v;
-    }
-    // paths per thread of the reverse sweep
-    static int reverseP()
-    {
-        static const int forced = [] { const char* e = std::getenv("CF_DUPIRE_P"); return e ? std::atoi(e) : 0; }();
-        return forced == 2 ? 2 : 4;
+        static const int forced = [] { const char* e = std::getenv("CF_DUPIRE_FWD_P"); return e ? std::atoi(e) : 0; }();
+        if (forced == 1 || forced == 2) return forced;
+        const uint64_t units2 = (n + 511) / 512 * 8;
+        return units2 * 8 <= uint64_t(g_sms) * cf::kFwdWarps * 5 ? 1 : 2;
     }
 
     // Runs are cut into launches of at most kFastChunk paths: the log-spot history of one launch is
@@ -339,19 +349,16 @@ struct cf_plan {
                     double* dPerPath, double* dPerAgg, cudaStream_t s)
     {
         const bool sob = rngKind == CF_RNG_SOBOL;
-        const int P = reverseP();
-        const int variant = forwardVariant();
-        const int fwdP = variant == 44 ? 4 : 2, fwdWarps = variant == 44 ? 16 : 24;
+        const int fwdP = forwardP(std::min<uint64_t>(n, kFastChunk)), fwdWarps = cf::kFwdWarps;
         const uint64_t quantum = 256ull * fwdP;
         const int histRow = (D + 3) / 4 * 4;
         const uint64_t maxChunk = std::min<uint64_t>(n, kFastChunk);
         const uint64_t maxPad = (maxChunk + quantum - 1) / quantum * quantum;
         const int maxUnitsF = int(maxPad / quantum) * 8;
-        const int gridF = std::min((maxUnitsF + fwdWarps - 1) / fwdWarps, g_sms);
+        const int gridF = std::min(maxUnitsF, g_sms);       // units are dealt round-robin: small runs still use every SM
         // reverse blocks own contiguous ranges of live-mask words (32 paths each), at most kRevMaxWords per block
-        const int maxUnitsR = int(maxPad / (32ull * P));
         const int minGridR = int((maxPad / 32 + cf::kRevMaxWords - 1) / cf::kRevMaxWords);
-        const int gridR = std::max(std::min((maxUnitsR + cf::kRevWarps - 1) / cf::kRevWarps, g_sms), minGridR);
+        const int gridR = std::max(int(std::min<uint64_t>(maxPad / 32, uint64_t(g_sms))), minGridR);
         const size_t tabLen = size_t(nTimes) * m;
         g_scratch.need(g_scratch.partial, size_t(gridF) * (size_t(nPay) + 1));
         if (aad) {
@@ -365,8 +372,8 @@ struct cf_plan {
         DKernel fwd;
         size_t smemF;
         fwd = cf::pick_dupire_forward(prdKind, aad, rngKind, fwdP);
-        smemF = fwdP == 4 ? cf::dupire_smem_fwd4<4>(D, m, dim, sob, nCells, 16).total : cf::dupire_smem_fwd4<2>(D, m, dim, sob, nCells, 24).total;
-        auto rev = cf::pick_dupire_reverse(prdKind, P);
+        smemF = fwdP == 2 ? cf::dupire_smem_fwd4<2>(D, m, dim, sob, nCells, fwdWarps).total : cf::dupire_smem_fwd4<1>(D, m, dim, sob, nCells, fwdWarps).total;
+        auto rev = cf::pick_dupire_reverse(prdKind);
         const size_t smemR = cf::dupire_smem_rev(D, m, nCells).total;
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fwd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
         if (aad) CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rev), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemR)));
@@ -389,7 +396,6 @@ struct cf_plan {
             CF_CUDA(cudaGetLastError());
             ++g_launches;
             if (aad) {
-                a.n_units = int(a.n_pad / (32ull * P));
                 rev<<<gridR, cf::kRevBlock, smemR, s>>>(a);
                 CF_CUDA(cudaGetLastError());
                 ++g_launches;
@@ -604,8 +610,7 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 p->flushOps.upload(ops.data(), ops.size());
                 CF_CUDA(cudaStreamSynchronize(nullptr));
                 const bool sob = rng->kind == CF_RNG_SOBOL;
-                if (cf::dupire_smem_fwd4<4>(D, m, p->dim, sob, nCells, 16).total > kFastSmemLimit
-                    || cf::dupire_smem_fwd4<2>(D, m, p->dim, sob, nCells, 24).total > kFastSmemLimit
+                if (cf::dupire_smem_fwd4<2>(D, m, p->dim, sob, nCells, cf::kFwdWarps).total > kFastSmemLimit
                     || cf::dupire_smem_rev(D, m, nCells).total > kFastSmemLimit) p->fast = false;
                 // Moro's branch test |u - 1/2| < 0.42 (gaussians.h:54) as a range of the RNG integer z: u(z) is
                 // monotone, so the central set is an interval [lo, hi]; searched with the device's own arithmetic
@@ -629,7 +634,7 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 d.n_steps = D; d.n_knots = m; d.n_slots = m + 2; d.n_times = p->nTimes;
                 d.ev_bits = p->stepBits.p; d.ev0 = mdl->is_event[0] ? 1 : 0;
                 d.spot = mdl->spot; d.shift = shift;
-                d.ab = p->ab.p; d.bk = p->bk.p; d.cells = p->cells.p; d.n_cells = nCells;
+                d.ab = p->ab.p; d.yrows = p->tabA.p; d.bk = p->bk.p; d.cells = p->cells.p; d.n_cells = nCells;
                 d.cell_scale = scale; d.cell_off = -x0 * scale;
                 d.wxy = p->c12.p; d.colxy = p->k12.p; d.flush_ops = p->flushOps.p;
                 d.n_payoffs = prd->n_payoffs; d.is_put = prd->is_put;
@@ -795,6 +800,7 @@ int cf_init(int n_devices, const int* device_ids)
         CF_CUDA(cudaSetDevice(device_ids[0]));
         g_device = device_ids[0];
         CF_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, g_device));
+        keep_pool_memory(g_device);
         g_launches = 0;
     });
 }
@@ -825,7 +831,12 @@ int cf_plan_create(const cf_model* mdl, const cf_product* prd, const cf_rng* rng
     });
 }
 
-void cf_plan_destroy(cf_plan* plan) { delete plan; }
+void cf_plan_destroy(cf_plan* plan)
+{
+    if (!plan) return;
+    cudaDeviceSynchronize();      // launches may be in flight on the caller's streams; the tables go back to the pool
+    delete plan;
+}
 
 size_t cf_plan_out_size(const cf_plan* plan, int aad) { return plan ? plan->outSize(aad != 0) : 0; }
 

@@ -16,8 +16,8 @@ KernelFn pick_path_kernel(int mdl, int prd, bool aad, int rng);
 MKernel pick_multi_kernel(int rng);
 // cf_pick_dlm.cu: displaced multi-asset model; amax 4 or 16; nullptr: MultiStats with AAD
 LKernel pick_dlm_kernel(int amax, int prd, bool aad, int rng);
-// cf_pick_dupire.cu: the north-star kernels; fwdP 2 (24 warps per block) or 4 (16 warps)
+// cf_pick_dupire.cu: the north-star kernels; fwdP = paths per thread of the forward kernel, 1 or 2 (kFwdWarps warps per block)
 DKernel pick_dupire_forward(int prd, bool aad, int rng, int fwdP);
-DKernel pick_dupire_reverse(int prd, int P);
+DKernel pick_dupire_reverse(int prd);
 
 }  // namespace cf

@@ -15,13 +15,12 @@ DKernel pickF(bool aad, int rng)
 DKernel pick_dupire_forward(int prd, bool aad, int rng, int fwdP)
 {
     const bool uoc = prd == CF_PRODUCT_UOC;
-    if (fwdP == 4) return uoc ? pickF<CF_PRODUCT_UOC, 4, 16>(aad, rng) : pickF<CF_PRODUCT_EUROPEAN, 4, 16>(aad, rng);
-    return uoc ? pickF<CF_PRODUCT_UOC, 2, 24>(aad, rng) : pickF<CF_PRODUCT_EUROPEAN, 2, 24>(aad, rng);
+    if (fwdP == 1) return uoc ? pickF<CF_PRODUCT_UOC, 1, kFwdWarps>(aad, rng) : pickF<CF_PRODUCT_EUROPEAN, 1, kFwdWarps>(aad, rng);
+    return uoc ? pickF<CF_PRODUCT_UOC, 2, kFwdWarps>(aad, rng) : pickF<CF_PRODUCT_EUROPEAN, 2, kFwdWarps>(aad, rng);
 }
 
-DKernel pick_dupire_reverse(int prd, int P)
+DKernel pick_dupire_reverse(int prd)
 {
-    if (prd == CF_PRODUCT_UOC) return P == 4 ? dupire_reverse_kernel<CF_PRODUCT_UOC, 4> : dupire_reverse_kernel<CF_PRODUCT_UOC, 2>;
-    return P == 4 ? dupire_reverse_kernel<CF_PRODUCT_EUROPEAN, 4> : dupire_reverse_kernel<CF_PRODUCT_EUROPEAN, 2>;
+    return prd == CF_PRODUCT_UOC ? dupire_reverse_kernel<CF_PRODUCT_UOC> : dupire_reverse_kernel<CF_PRODUCT_EUROPEAN>;
 }
 }  // namespace cf

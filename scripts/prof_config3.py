@@ -16,6 +16,8 @@ ptl = R.uoc_timeline(3.0, 1.0 / 52)
 tab = R.DupireTables(100, spots, times, vols, 0.25, ptl)
 mdl = eng.dupire_model(100.0, tab.log_spots, tab.interp_vols, tab.common, len(ptl), time_map=tab.time_map())
 prd = eng.uoc(120.0, 150.0, float(np.exp(np.log(100.0)) * 0.01), len(ptl))
+if os.environ.get("CF_PROF_BARRIER"):
+    prd = eng.uoc(120.0, float(os.environ["CF_PROF_BARRIER"]), float(np.exp(np.log(100.0)) * 0.01), len(ptl))
 rg = eng.rng("sobol")
 plan = C.c_void_p()
 eng._chk(eng.lib.cf_plan_create(C.byref(mdl), C.byref(prd), C.byref(rg), C.byref(plan)))

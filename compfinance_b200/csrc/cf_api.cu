@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -901,15 +902,22 @@ int cf_run_aad(const cf_model* mdl, const cf_product* prd, const cf_rng* rng, ui
 {
     return guarded([&] {
         if (!payoff_weights || !payoff_sums || !agg_sum || !table_adjoints) throw CfError("cf_run_aad: null output");
+        static const bool timing = std::getenv("CF_TIMING") != nullptr;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        const auto t0 = now();
         auto plan = make_plan(mdl, prd, rng);
+        const auto t1 = now();
         DevBuf<double> dOut, dPer, dAgg;
         const size_t nOut = plan->outSize(true);
         dOut.alloc(nOut);
         if (per_path_payoffs) dPer.alloc(n_paths * plan->nPay);
         if (per_path_agg) dAgg.alloc(n_paths);
         plan->launch(true, payoff_weights, first_path, n_paths, dOut.p, dPer.p, dAgg.p, nullptr);
+        const auto t2 = now();
         std::vector<double> h(nOut);
         CF_CUDA(cudaMemcpy(h.data(), dOut.p, sizeof(double) * nOut, cudaMemcpyDeviceToHost));
+        if (timing) std::fprintf(stderr, "cf_run_aad: make_plan %.0f us, launch calls %.0f us, wait + copy back %.0f us\n", us(t0, t1), us(t1, t2), us(t2, now()));
         std::memcpy(payoff_sums, h.data(), sizeof(double) * plan->nPay);
         *agg_sum = h[plan->nPay];
         std::memcpy(table_adjoints, h.data() + plan->nPay + 1, sizeof(double) * plan->nAdj);

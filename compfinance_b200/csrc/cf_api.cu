@@ -71,27 +71,74 @@ void ensure_init()
     keep_pool_memory(dev);
 }
 
+// Table uploads of one plan are batched: while an UploadBatch is open, upload() copies the host data into a pinned
+// staging block and hands out a slice of one device arena; closing the batch sends everything in a single
+// cudaMemcpyAsync (a plan has a few dozen tables of a few KB: one copy each costs more than the kernels save).
+struct UploadBatch {
+    static constexpr size_t kCapacity = size_t(4) << 20;
+    unsigned char* dev = nullptr;       // device arena of this batch (owned by the plan)
+    size_t used = 0;
+    static UploadBatch*& current() { static thread_local UploadBatch* b = nullptr; return b; }
+    static unsigned char*& staging() { static unsigned char* h = nullptr; return h; }
+    static cudaEvent_t& copied() { static cudaEvent_t e = nullptr; return e; }
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owned = true;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    // stream-ordered allocations from the device's default pool (kept by the pool after the first call: the tables of
-    // a plan are a few dozen small buffers, and a cudaMalloc / cudaFree pair each would cost more than the kernels)
-    ~DevBuf() { if (p) cudaFreeAsync(p, nullptr); }
+    // stream-ordered allocations from the device's default pool (kept by the pool after the first call)
+    ~DevBuf() { release(); }
+    void release() { if (p && owned) cudaFreeAsync(p, nullptr); p = nullptr; owned = true; }
     void alloc(size_t count)
     {
-        if (p) { cudaFreeAsync(p, nullptr); p = nullptr; }
+        release();
         n = count;
         if (count) CF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), nullptr));
     }
     void upload(const T* src, size_t count, cudaStream_t s = nullptr)
     {
+        UploadBatch* b = UploadBatch::current();
+        const size_t bytes = count * sizeof(T), off = b ? (b->used + 255) / 256 * 256 : 0;
+        if (b && count && off + bytes <= UploadBatch::kCapacity) {
+            release();
+            std::memcpy(UploadBatch::staging() + off, src, bytes);
+            p = reinterpret_cast<T*>(b->dev + off); n = count; owned = false;
+            b->used = off + bytes;
+            return;
+        }
         alloc(count);
-        if (count) CF_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        if (count) CF_CUDA(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s));
     }
+};
+
+// Opens a batch on construction, sends it on close().  arena: the plan's buffer that owns the device block.
+struct UploadScope {
+    UploadBatch batch;
+    explicit UploadScope(DevBuf<unsigned char>& arena)
+    {
+        if (!UploadBatch::staging()) {
+            CF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&UploadBatch::staging()), UploadBatch::kCapacity, cudaHostAllocDefault));
+            CF_CUDA(cudaEventCreateWithFlags(&UploadBatch::copied(), cudaEventDisableTiming));
+        } else {
+            CF_CUDA(cudaEventSynchronize(UploadBatch::copied()));     // the previous batch has left the staging block
+        }
+        arena.alloc(UploadBatch::kCapacity);
+        batch.dev = arena.p;
+        UploadBatch::current() = &batch;
+    }
+    void close()
+    {
+        if (UploadBatch::current() != &batch) return;
+        UploadBatch::current() = nullptr;
+        if (batch.used) CF_CUDA(cudaMemcpyAsync(batch.dev, UploadBatch::staging(), batch.used, cudaMemcpyHostToDevice, nullptr));
+        CF_CUDA(cudaEventRecord(UploadBatch::copied(), nullptr));
+    }
+    ~UploadScope() { if (UploadBatch::current() == &batch) UploadBatch::current() = nullptr; }
 };
 
 // Scratch shared by all plans of the process (one run at a time per context): path history,
@@ -194,6 +241,8 @@ struct cf_plan {
     int mdlKind = 0, prdKind = 0, rngKind = 0;
     int D = 0, m = 0, E = 0, dim = 0, nPay = 0;
     size_t nAdj = 0;           // table adjoints including the spot leaf
+    DevBuf<unsigned char> arena;      // one device block for all the tables uploaded by make_plan
+    bool tablesInFlight = true;       // the first launch orders its stream after the table upload (null stream)
     cf::KArgs base{};
     DevBuf<uint8_t> isEvent;
     DevBuf<double> tabA, tabB, num, ff, disc;
@@ -245,6 +294,10 @@ struct cf_plan {
     {
         if (n == 0) throw CfError("cf_b200: n_paths must be > 0");
         if (rngKind == CF_RNG_SOBOL && first + n > 0xffffffffull) throw CfError("cf_b200: Sobol index exceeds 2^32 - 1");
+        if (tablesInFlight) {
+            if (UploadBatch::copied()) CF_CUDA(cudaStreamWaitEvent(s, UploadBatch::copied(), 0));
+            tablesInFlight = false;
+        }
         const uint64_t nb64 = (n + cf::kBlock - 1) / cf::kBlock;
         if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
         const int nBatches = int(nb64);
@@ -419,6 +472,7 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     ensure_init();
     validate(mdl, prd, rng);
     auto p = std::make_unique<cf_plan>();
+    UploadScope uploads(p->arena);
     p->mdlKind = mdl->kind; p->prdKind = prd->kind; p->rngKind = rng->kind;
     p->D = mdl->n_steps; p->E = mdl->n_events; p->dim = mdl->n_steps * mdl->n_assets;
     p->m = mdl->kind == CF_MODEL_DUPIRE ? mdl->n_knots : 0;
@@ -465,7 +519,6 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
             }
             p->lutN = n + 1;
             p->lut.upload(lut.data(), lut.size());
-            CF_CUDA(cudaStreamSynchronize(nullptr));
             p->base.lut_x0 = mdl->log_spots[0];
             p->base.lut_scale = scale;
         }
@@ -500,7 +553,6 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
         const auto jump = cf::mrg_jump_matrices(uint64_t(p->dim));
         p->mrgJump.upload(jump.data(), jump.size());
     }
-    CF_CUDA(cudaStreamSynchronize(nullptr));   // staging vectors above go out of scope
     cf::KArgs& a = p->base;
     a.seed1 = rng->seed1; a.seed2 = rng->seed2; a.dim = p->dim;
     a.sobol_dir = p->sobolDir.p; a.mrg_jump = p->mrgJump.p;
@@ -520,7 +572,6 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
                     throw CfError("cf_b200: Dupire time map column out of range");
             p->tk1.upload(mdl->time_col1, size_t(p->D)); p->tk2.upload(mdl->time_col2, size_t(p->D));
             p->tc1.upload(mdl->time_w1, size_t(p->D)); p->tc2.upload(mdl->time_w2, size_t(p->D));
-            CF_CUDA(cudaStreamSynchronize(nullptr));
         }
         // The fast kernels (cf_dupire.cuh) need: 2..30 knots (32 accumulator rows per lane), vols bounded away
         // from 0 (g - v is recovered by a division), a timeline that ends on an event date, tables that fit.
@@ -609,8 +660,7 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 p->c12.upload(wxy.data(), wxy.size());
                 p->k12.upload(colxy.data(), colxy.size());
                 p->flushOps.upload(ops.data(), ops.size());
-                CF_CUDA(cudaStreamSynchronize(nullptr));
-                const bool sob = rng->kind == CF_RNG_SOBOL;
+                    const bool sob = rng->kind == CF_RNG_SOBOL;
                 if (cf::dupire_smem_fwd4<2>(D, m, p->dim, sob, nCells, cf::kFwdWarps).total > kFastSmemLimit
                     || cf::dupire_smem_rev(D, m, nCells).total > kFastSmemLimit) p->fast = false;
                 // Moro's branch test |u - 1/2| < 0.42 (gaussians.h:54) as a range of the RNG integer z: u(z) is
@@ -647,6 +697,7 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     a.strike = prd->strike; a.barrier = prd->barrier; a.smooth = prd->smooth;
     a.strikes = p->eStrikes.p; a.strike_off = p->eOff.p;
     if (prd->kind == CF_PRODUCT_EUROPEANS) p->fast = false;      // many payoffs: generic kernel
+    uploads.close();
     return p;
 }
 

@@ -17,7 +17,7 @@ _ip = C.POINTER(C.c_int)
 
 EXPORTED = [
     "cfx_last_error", "cfx_init", "cfx_set_system_time", "cfx_put_black_scholes", "cfx_put_dupire",
-    "cfx_put_european", "cfx_put_barrier", "cfx_put_europeans", "cfx_put_displaced", "cfx_put_multistats",
+    "cfx_put_european", "cfx_put_barrier", "cfx_put_contingent", "cfx_put_europeans", "cfx_put_displaced", "cfx_put_multistats",
     "cfx_put_baskets", "cfx_put_autocall", "cfx_num_payoffs", "cfx_num_params",
     "cfx_payoff_labels", "cfx_param_labels", "cfx_product_timeline", "cfx_value", "cfx_simul_paths",
     "cfx_aad_risk_one", "cfx_simul_aad_paths", "cfx_aad_risk_aggregate", "cfx_aad_risk_multi", "cfx_bump_risk", "cfx_dupire_aad_risk", "cfx_dupire_calib", "cfx_dupire_superbucket",
@@ -65,6 +65,11 @@ class CompFinance:
 
     def put_european(self, strike, exercise, settlement, id_):
         self._chk(self.lib.cfx_put_european(C.c_double(strike), C.c_double(exercise), C.c_double(settlement), id_.encode()))
+
+    def put_contingent(self, coupon, maturity, pay_freq, smooth, id_):
+        """xPutContingent (xlExport.cpp:320): contingent floater, Black-Scholes only on the device."""
+        self._chk(self.lib.cfx_put_contingent(C.c_double(coupon), C.c_double(maturity), C.c_double(pay_freq),
+                                              C.c_double(smooth), id_.encode()))
 
     def put_barrier(self, strike, barrier, maturity, freq, smooth, call_put, id_):
         self._chk(self.lib.cfx_put_barrier(C.c_double(strike), C.c_double(barrier), C.c_double(maturity),

@@ -31,7 +31,7 @@ class cf_model(C.Structure):
         ("kind", C.c_int32), ("n_assets", C.c_int32), ("n_steps", C.c_int32), ("n_events", C.c_int32),
         ("is_event", _u8p), ("spot", C.c_double),
         ("bs_drifts", _dp), ("bs_stds", _dp),
-        ("numeraires", _dp), ("fwd_factors", _dp), ("discounts", _dp),
+        ("numeraires", _dp), ("fwd_factors", _dp), ("discounts", _dp), ("libors", _dp),
         ("n_knots", C.c_int32), ("log_spots", _dp), ("interp_vols", _dp),
         ("n_times", C.c_int32), ("time_col1", _ip), ("time_col2", _ip), ("time_w1", _dp), ("time_w2", _dp),
         ("dlm_spots", _dp), ("dlm_chol", _dp), ("dlm_alphas", _dp), ("dlm_dynamics", _ip),

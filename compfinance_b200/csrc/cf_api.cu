@@ -175,7 +175,7 @@ size_t adj_size(const cf_model* mdl)
             return 1 + size_t(mdl->n_knots) * mdl->n_times;
         return 1 + size_t(mdl->n_steps) * mdl->n_knots;
     }
-    if (mdl->kind == CF_MODEL_BS) return 1 + 2 * size_t(mdl->n_steps) + 3 * size_t(mdl->n_events);
+    if (mdl->kind == CF_MODEL_BS) return 1 + 2 * size_t(mdl->n_steps) + 4 * size_t(mdl->n_events);
     if (mdl->kind == CF_MODEL_DISPLACED) return size_t(cf::dlm_adj_size(mdl->n_assets, mdl->n_steps, mdl->n_events));
     throw CfError("cf_b200: model kind not implemented");
 }
@@ -222,6 +222,10 @@ void validate(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
         if (mdl->is_event[0]) throw CfError("cf_b200: an Autocall has no sample today");
     } else if (prd->kind == CF_PRODUCT_BASKETS) {
         if (prd->n_events != 1 || prd->n_payoffs < 1 || !prd->strikes || !prd->weights) throw CfError("cf_b200: Baskets needs weights, strikes and a single event");
+    } else if (prd->kind == CF_PRODUCT_CONTINGENT) {
+        if (mdl->kind != CF_MODEL_BS) throw CfError("cf_b200: the contingent bond runs under Black-Scholes only on the device");
+        if (prd->n_payoffs != 1 || prd->n_events < 2 || !prd->event_dt) throw CfError("cf_b200: ContingentBond needs at least one period, the coverages and has one payoff");
+        if (!(prd->smooth >= 0)) throw CfError("cf_b200: ContingentBond smooth must be >= 0");
     } else if (prd->kind == CF_PRODUCT_MULTISTATS) {
         const int A = mdl->n_assets, E = prd->n_events;
         if (prd->n_payoffs != (2 * E - 1) * (A + A * (A + 1) / 2)) throw CfError("cf_b200: MultiStats payoff count does not match assets and dates");
@@ -245,7 +249,7 @@ struct cf_plan {
     bool tablesInFlight = true;       // the first launch orders its stream after the table upload (null stream)
     cf::KArgs base{};
     DevBuf<uint8_t> isEvent;
-    DevBuf<double> tabA, tabB, num, ff, disc;
+    DevBuf<double> tabA, tabB, num, ff, disc, libors, eventDt;
     DevBuf<uint32_t> sobolDir;
     DevBuf<uint64_t> mrgJump;
     DevBuf<uint8_t> lut;
@@ -542,6 +546,8 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     if (mdl->numeraires && mdl->kind != CF_MODEL_DISPLACED) p->num.upload(mdl->numeraires, size_t(p->E));
     if (mdl->fwd_factors) p->ff.upload(mdl->fwd_factors, size_t(p->E));
     if (mdl->discounts) p->disc.upload(mdl->discounts, size_t(p->E));
+    if (mdl->libors && mdl->kind == CF_MODEL_BS) p->libors.upload(mdl->libors, size_t(p->E));
+    if (prd->kind == CF_PRODUCT_CONTINGENT) p->eventDt.upload(prd->event_dt, size_t(prd->n_events) - 1);
     if (rng->kind == CF_RNG_SOBOL) {
         const auto& full = cf::sobol_direction_table();
         const int nd = cf::sobol_max_dim();
@@ -561,7 +567,7 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     a.n_steps = p->D; a.n_events = p->E; a.n_knots = p->m;
     a.is_event = p->isEvent.p; a.spot = mdl->spot;
     a.tabA = p->tabA.p; a.tabB = p->tabB.p;
-    a.numeraires = p->num.p; a.fwd_factors = p->ff.p; a.discounts = p->disc.p;
+    a.numeraires = p->num.p; a.fwd_factors = p->ff.p; a.discounts = p->disc.p; a.libors = p->libors.p;
     a.lut = p->lut.p; a.lut_n = p->lutN; a.store_g = p->storeG;
     if (mdl->kind == CF_MODEL_DUPIRE) {
         p->hasTimeMap = mdl->n_times > 0 && mdl->time_col1 && mdl->time_col2 && mdl->time_w1 && mdl->time_w2;
@@ -694,7 +700,7 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
         }
     }
     a.n_payoffs = prd->n_payoffs; a.is_put = prd->is_put;
-    a.strike = prd->strike; a.barrier = prd->barrier; a.smooth = prd->smooth;
+    a.strike = prd->strike; a.barrier = prd->barrier; a.smooth = prd->smooth; a.coupon = prd->coupon; a.event_dt = p->eventDt.p;
     a.strikes = p->eStrikes.p; a.strike_off = p->eOff.p;
     if (prd->kind == CF_PRODUCT_EUROPEANS) p->fast = false;      // many payoffs: generic kernel
     uploads.close();

@@ -47,6 +47,7 @@ struct KArgs {
     const double* numeraires;      // [n_events] or null (BS only; Dupire leaves the Sample defaults)
     const double* fwd_factors;     // [n_events] or null
     const double* discounts;       // [n_events] or null
+    const double* libors;          // [n_events] or null (first libor of each event date)
     // Dupire bucket lookup: cell = (L - lut_x0) * lut_scale, lut[cell] = #knots <= left edge of cell
     const uint8_t* lut;
     int      lut_n;                // 0 = no table, use binary search
@@ -54,7 +55,8 @@ struct KArgs {
     int      store_g;              // 1: keep g_i in the history (needed when some interp_vol ~ 0)
     // product
     int      n_payoffs, is_put;
-    double   strike, barrier, smooth;
+    double   strike, barrier, smooth, coupon;
+    const double* event_dt;        // ContingentBond: coverage of the period starting at event e
     double   w[kMaxPay];           // payoff weights of the aggregate (AAD)
     // Europeans (mcPrd.h:290-401): strikes of event e are strikes[strike_off[e] .. strike_off[e+1]), weights in memory
     const double*  strikes;
@@ -82,17 +84,19 @@ struct LogSpotSrc {      // Dupire: forwards[0][0] = spot = exp(L), numeraire = 
     __device__ double fwd() { if (!have) { S = exp(L); have = true; } return S; }
     __device__ double num() const { return 1.0; }
     __device__ double disc() const { return 1.0; }
+    __device__ double lib() const { return 0.0; }
 };
-struct FwdSrc {          // Black-Scholes: forward = S * ff[e], numeraire / discount from tables
+struct FwdSrc {          // Black-Scholes: forward = S * ff[e], numeraire / discount / libor from tables
     static constexpr bool kHasLog = false;
-    double F, N, Dsc;
-    __device__ FwdSrc(double f, double n, double d) : F(f), N(n), Dsc(d) {}
+    double F, N, Dsc, Lib;
+    __device__ FwdSrc(double f, double n, double d, double l = 0.0) : F(f), N(n), Dsc(d), Lib(l) {}
     __device__ double logFwd() const { return 0.0; }
     __device__ double fwd() { return F; }
     __device__ double num() const { return N; }
     __device__ double disc() const { return Dsc; }
+    __device__ double lib() const { return Lib; }
 };
-struct SampleAdj { double fwd, num, disc; };
+struct SampleAdj { double fwd, num, disc, lib; };
 
 // Sink for products with many payoffs (Europeans): payoff k of this path goes to the warp's row of payoff
 // sums (fixed order: lanes by shuffle tree, warps combined at the end of the kernel), to the aggregate
@@ -128,9 +132,9 @@ template <> struct Product<CF_PRODUCT_EUROPEAN> {
     }
     __device__ void payoffs(double* out) const { out[0] = pay; }
     __device__ void begin_reverse(const double* w) { wbar = w[0]; }
-    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s)
+    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s, double /*prevFwd*/)
     {
-        SampleAdj r = {0.0, 0.0, 0.0};
+        SampleAdj r = {0.0, 0.0, 0.0, 0.0};
         if (e == 0) {
             const double F = s.fwd();
             const double intrinsic = fmax(F - strike, 0.0);
@@ -180,9 +184,9 @@ template <> struct Product<CF_PRODUCT_UOC> {
         abar = killed ? 0.0 : w[0] * euro;      // a killed `alive` is a fresh leaf: nothing flows
         aliveCur = alive;
     }
-    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s)
+    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s, double /*prevFwd*/)
     {
-        SampleAdj r = {0.0, 0.0, 0.0};
+        SampleAdj r = {0.0, 0.0, 0.0, 0.0};
         if (e == nEvents - 1) {
             const double F = s.fwd();
             const double x = isPut ? strike - F : F - strike;
@@ -219,9 +223,9 @@ template <> struct Product<CF_PRODUCT_EUROPEANS> {
     }
     __device__ void payoffs(double*) const {}
     __device__ void begin_reverse(const double*) {}
-    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s)
+    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s, double /*prevFwd*/)
     {
-        SampleAdj r = {0.0, 0.0, 0.0};
+        SampleAdj r = {0.0, 0.0, 0.0, 0.0};
         const double F = s.fwd(), num = s.num();
         const int k1 = __ldg(off + e + 1);
         for (int k = __ldg(off + e); k < k1; ++k) {
@@ -231,6 +235,52 @@ template <> struct Product<CF_PRODUCT_EUROPEANS> {
                 r.fwd += wk / num;
                 r.num -= wk * x / (num * num);
             }
+        }
+        return r;
+    }
+};
+
+// Contingent floater, mcPrd.h:513-572: per period [T_e-1, T_e] the coupon (libor(T_e-1, T_e) + cpn) * coverage is paid
+// at T_e if the asset went up over the period, with a smoothed digital of half-width `smooth`; redemption at maturity.
+template <> struct Product<CF_PRODUCT_CONTINGENT> {
+    double smooth, twoSmooth, cpn, pay, s0, libPrev, wbar, carryFwd, carryLib;
+    const double* dt;
+    const double* libors;
+    __device__ void init(const KArgs& a)
+    {
+        smooth = a.smooth; twoSmooth = 2 * a.smooth; cpn = a.coupon; dt = a.event_dt; libors = a.libors;
+        pay = 0.0; s0 = 0.0; libPrev = 0.0;
+    }
+    __device__ double digital(double d) const
+    {
+        if (d > smooth) return 1.0;
+        if (d < -smooth) return 0.0;
+        return (d + smooth) / twoSmooth;                      // "fuzzy" edge: interpolate (mcPrd.h:556-559)
+    }
+    template <class Src> __device__ void observe(int e, int nEvents, Src& s, PayCtx&)
+    {
+        const double s1 = s.fwd();
+        if (e > 0) pay += digital(s1 - s0) * (libPrev + cpn) * __ldg(dt + e - 1) / s.num();
+        if (e == nEvents - 1) pay += 1.0 / s.num();           // redemption at maturity
+        s0 = s1; libPrev = s.lib();
+    }
+    __device__ void payoffs(double* out) const { out[0] = pay; }
+    __device__ void begin_reverse(const double* w) { wbar = w[0]; carryFwd = 0.0; carryLib = 0.0; }
+    template <class Src> __device__ SampleAdj reverse(int e, int nEvents, Src& s, double prevFwd)
+    {
+        // what the period starting here (paid at event e + 1) sent back to this date's spot and libor
+        SampleAdj r = {carryFwd, 0.0, 0.0, carryLib};
+        carryFwd = 0.0; carryLib = 0.0;
+        const double num = s.num();
+        if (e == nEvents - 1) r.num -= wbar / (num * num);
+        if (e > 0) {
+            const double d = s.fwd() - prevFwd, lib = libors ? __ldg(libors + e - 1) : 0.0, cov = __ldg(dt + e - 1);
+            const double dig = digital(d);
+            const double ddig = (d > smooth || d < -smooth) ? 0.0 : 1.0 / twoSmooth;
+            r.num -= wbar * (dig * (lib + cpn) * cov / num) / num;
+            const double g = wbar * ddig * (lib + cpn) * cov / num;
+            r.fwd += g; carryFwd = -g;
+            carryLib = wbar * dig * cov / num;
         }
         return r;
     }
@@ -264,7 +314,7 @@ __host__ __device__ inline int table_b_size(int nSteps, int nKnots) { return MDL
 template <int MDL>
 __host__ __device__ inline int adj_table_size(int nSteps, int nKnots, int nEvents)
 {
-    return MDL == CF_MODEL_DUPIRE ? nSteps * nKnots : 2 * nSteps + 3 * nEvents;
+    return MDL == CF_MODEL_DUPIRE ? nSteps * nKnots : 2 * nSteps + 4 * nEvents;
 }
 template <int MDL>
 __host__ __device__ inline int row_len(int nKnots) { return MDL == CF_MODEL_DUPIRE ? (nKnots > 1 ? nKnots - 1 : 1) : 3; }
@@ -490,7 +540,8 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
         auto bsSample = [&](int e, double spotNow) -> FwdSrc {
             return FwdSrc(a.fwd_factors ? spotNow * __ldg(a.fwd_factors + e) : spotNow,
                           a.numeraires ? __ldg(a.numeraires + e) : 1.0,
-                          a.discounts ? __ldg(a.discounts + e) : 1.0);
+                          a.discounts ? __ldg(a.discounts + e) : 1.0,
+                          a.libors ? __ldg(a.libors + e) : 0.0);
         };
 
         // ---- forward: generatePath + payoffs
@@ -563,7 +614,7 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
                 if (kDupire) {
                     if (sm.isev[i + 1]) {
                         LogSpotSrc s(X);
-                        const SampleAdj sa = prd.reverse(er, E, s);
+                        const SampleAdj sa = prd.reverse(er, E, s, 0.0);
                         if (sa.fwd != 0.0) Xbar += sa.fwd * s.fwd();   // dS/dL = S
                         --er;
                     }
@@ -601,8 +652,11 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
                     // BS: X currently holds S_{i+1}
                     const double g = histG[size_t(i) * nSlots + slot];
                     const double S1 = X;
+                    const double S0 = (i > 0) ? histL[size_t(i - 1) * nSlots + slot] : a.spot;
                     FwdSrc smp = bsSample(er, S1);
-                    const SampleAdj sa = prd.reverse(er, E, smp);
+                    // forward sampled on the previous event date (products that compare consecutive samples)
+                    const double prevFwd = (er > 0 && a.fwd_factors) ? S0 * __ldg(a.fwd_factors + er - 1) : S0;
+                    const SampleAdj sa = prd.reverse(er, E, smp, prevFwd);
                     const double ff = a.fwd_factors ? __ldg(a.fwd_factors + er) : 1.0;
                     Xbar += sa.fwd * ff;
                     const double abar = valid ? Xbar * S1 : 0.0;           // adjoint of drift_i + std_i g_i
@@ -610,12 +664,12 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
                     // dense per-step values: drift, std | numeraire, fwd factor, discount of event er
                     double v0 = warp_sum(abar), v1 = warp_sum(abar * g);
                     double v2 = warp_sum(valid ? sa.num : 0.0), v3 = warp_sum(valid ? sa.fwd * S1 : 0.0);
-                    double v4 = warp_sum(valid ? sa.disc : 0.0);
-                    if (lane == 0) { myRow[0] = make_double2(v0, v1); myRow[1] = make_double2(v2, v3); myRow[2] = make_double2(v4, 0.0); }
+                    double v4 = warp_sum(valid ? sa.disc : 0.0), v5 = warp_sum(valid ? sa.lib : 0.0);
+                    if (lane == 0) { myRow[0] = make_double2(v0, v1); myRow[1] = make_double2(v2, v3); myRow[2] = make_double2(v4, v5); }
                     Xbar *= ei;
-                    X = (i > 0) ? histL[size_t(i - 1) * nSlots + slot] : a.spot;
+                    X = S0;
                     __syncthreads();
-                    if (tid < 5) {
+                    if (tid < 6) {
                         double s = 0.0;
                         const double2* rows = sm.wrow + size_t(buf * kWarps) * rowLen;
                         for (int w = 0; w < kWarps; ++w) {
@@ -632,19 +686,19 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
             if (sm.isev[0]) {
                 if (kDupire) {
                     LogSpotSrc s(X);
-                    const SampleAdj sa = prd.reverse(0, E, s);
+                    const SampleAdj sa = prd.reverse(0, E, s, 0.0);
                     if (sa.fwd != 0.0) Xbar += sa.fwd * s.fwd();
                 } else {
                     FwdSrc smp = bsSample(0, X);
-                    const SampleAdj sa = prd.reverse(0, E, smp);
+                    const SampleAdj sa = prd.reverse(0, E, smp, 0.0);
                     const double ff = a.fwd_factors ? __ldg(a.fwd_factors) : 1.0;
                     Xbar += sa.fwd * ff;
                     double v2 = warp_sum(valid ? sa.num : 0.0), v3 = warp_sum(valid ? sa.fwd * X : 0.0);
-                    double v4 = warp_sum(valid ? sa.disc : 0.0);
+                    double v4 = warp_sum(valid ? sa.disc : 0.0), v5 = warp_sum(valid ? sa.lib : 0.0);
                     __syncthreads();
-                    if (lane == 0) { sm.wrow[warp * rowLen] = make_double2(v2, v3); sm.wrow[warp * rowLen + 1] = make_double2(v4, 0.0); }
+                    if (lane == 0) { sm.wrow[warp * rowLen] = make_double2(v2, v3); sm.wrow[warp * rowLen + 1] = make_double2(v4, v5); }
                     __syncthreads();
-                    if (tid < 3) {
+                    if (tid < 4) {
                         double s = 0.0;
                         for (int w = 0; w < kWarps; ++w) {
                             const double2 q = sm.wrow[w * rowLen + (tid >> 1)];

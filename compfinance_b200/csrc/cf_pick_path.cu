@@ -21,6 +21,7 @@ KernelFn pick_path_kernel(int mdl, int prd, bool aad, int rng)
     if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_UOC) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_UOC>(aad, rng);
     if (mdl == CF_MODEL_BS && prd == CF_PRODUCT_EUROPEANS) return pick2<CF_MODEL_BS, CF_PRODUCT_EUROPEANS>(aad, rng);
     if (mdl == CF_MODEL_DUPIRE && prd == CF_PRODUCT_EUROPEANS) return pick2<CF_MODEL_DUPIRE, CF_PRODUCT_EUROPEANS>(aad, rng);
+    if (mdl == CF_MODEL_BS && prd == CF_PRODUCT_CONTINGENT) return pick2<CF_MODEL_BS, CF_PRODUCT_CONTINGENT>(aad, rng);
     return nullptr;
 }
 

@@ -97,7 +97,7 @@ struct ModelImage
 {
     cf_model pod{};
     std::vector<uint8_t> isEvent;
-    std::vector<double>  tabA, tabB, numeraires, fwdFactors, discounts;
+    std::vector<double>  tabA, tabB, numeraires, fwdFactors, discounts, libors;
     std::vector<int32_t> col1, col2;
     std::vector<double>  w1, w2;
     // value of forwards[0][0] on the first sample when that sample is today (UOC smoothing, mcPrd.h:247)

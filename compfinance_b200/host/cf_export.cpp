@@ -86,6 +86,11 @@ int cfx_put_barrier(double strike, double barrier, double maturity, double monit
     return guarded([&] { putBarrier(strike, barrier, maturity, monitorFreq, smooth, callPut != 0, id); });
 }
 
+int cfx_put_contingent(double coupon, double maturity, double payFreq, double smooth, const char* id)
+{
+    return guarded([&] { putContingent(coupon, maturity, payFreq, smooth, id); });
+}
+
 int cfx_put_europeans(const double* maturities, const double* strikes, int n, const char* id)
 {
     return guarded([&] {

@@ -107,9 +107,9 @@ public:
 
     size_t simDim() const override { return myTimeline.size() - 1; }
 
-    // Device image: drifts / stds per step; per event date the numeraire, first forward factor and
-    // first discount (what European / UOC / Europeans read: forwards[0][0], discounts[0], numeraire).
-    // Adjoint layout: [spot, drift[D], std[D], numeraire[E], fwd factor[E], discount[E]].
+    // Device image: drifts / stds per step; per event date the numeraire, first forward factor, first
+    // discount and first libor (what the single-asset products read: forwards[0][0], discounts[0],
+    // libors[0], numeraire).  Adjoint layout: [spot, drift[D], std[D], numeraire[E], fwd factor[E], discount[E], libor[E]].
     bool deviceImage(ModelImage& img, const std::vector<Time>& productTimeline, const std::vector<SampleDef>& defline) override
     {
         if (mySpotMeasure) return false;      // numeraire depends on the path under the spot measure
@@ -120,10 +120,10 @@ public:
         img.isEvent[0] = myTodayOnTimeline ? 1 : 0;
         img.tabA.resize(D); img.tabB.resize(D);
         for (size_t i = 0; i < D; ++i) { img.tabA[i] = cfValue(myDrifts[i]); img.tabB[i] = cfValue(myStds[i]); }
-        img.numeraires.assign(E, 1.0); img.fwdFactors.assign(E, 1.0); img.discounts.assign(E, 1.0);
+        img.numeraires.assign(E, 1.0); img.fwdFactors.assign(E, 1.0); img.discounts.assign(E, 1.0); img.libors.assign(E, 0.0);
         for (size_t e = 0; e < E; ++e) {
-            if (defline[e].liborDefs.size() > 0) return false;                       // libors: not on the device
-            if (defline[e].forwardMats.front().size() > 1 || defline[e].discountMats.size() > 1) return false;
+            if (defline[e].forwardMats.front().size() > 1 || defline[e].discountMats.size() > 1 || defline[e].liborDefs.size() > 1) return false;
+            if (!myLibors[e].empty()) img.libors[e] = cfValue(myLibors[e][0]);
             if (defline[e].numeraire) img.numeraires[e] = cfValue(myNumeraires[e]);
             if (!myForwardFactors[e].empty()) img.fwdFactors[e] = cfValue(myForwardFactors[e][0]);
             if (!myDiscounts[e].empty()) img.discounts[e] = cfValue(myDiscounts[e][0]);
@@ -133,17 +133,19 @@ public:
         p.is_event = img.isEvent.data(); p.spot = cfValue(mySpot);
         p.bs_drifts = img.tabA.data(); p.bs_stds = img.tabB.data();
         p.numeraires = img.numeraires.data(); p.fwd_factors = img.fwdFactors.data(); p.discounts = img.discounts.data();
+        p.libors = img.libors.data();
         img.firstSampleIsToday = myTodayOnTimeline;
         img.firstSampleForward = cfValue(mySpot) * img.fwdFactors[0];
         if constexpr (std::is_same<T, Number>::value) {
             auto& t = img.adjointTargets;
-            t.assign(1 + 2 * D + 3 * E, nullptr);
+            t.assign(1 + 2 * D + 4 * E, nullptr);
             t[0] = &mySpot;
             for (size_t i = 0; i < D; ++i) { t[1 + i] = &myDrifts[i]; t[1 + D + i] = &myStds[i]; }
             for (size_t e = 0; e < E; ++e) {
                 if (defline[e].numeraire) t[1 + 2 * D + e] = &myNumeraires[e];
                 if (!myForwardFactors[e].empty()) t[1 + 2 * D + E + e] = &myForwardFactors[e][0];
                 if (!myDiscounts[e].empty()) t[1 + 2 * D + 2 * E + e] = &myDiscounts[e][0];
+                if (!myLibors[e].empty()) t[1 + 2 * D + 3 * E + e] = &myLibors[e][0];
             }
             for (auto*& q : t) if (q && !q->onTape()) q = nullptr;     // constants carry no adjoint
         }

@@ -120,6 +120,68 @@ public:
     }
 };
 
+// Contingent floater (mcPrd.h:404-574): every period pays (libor + coupon) x coverage at its end if the asset went
+// up over the period (smoothed digital), plus redemption at maturity.  One payoff.
+template <class T>
+class ContingentBond : public Product<T>
+{
+    Time   myMaturity;
+    double myCpn, mySmooth;
+    std::vector<Time>        myTimeline;
+    std::vector<SampleDef>   myDefline;
+    std::vector<std::string> myLabels;
+    std::vector<double>      myDt;              // coverage of the period starting at timeline point i
+
+public:
+    ContingentBond(const Time maturity, const double cpn, const Time payFreq, const double smooth)
+        : myMaturity(maturity), myCpn(cpn), mySmooth(smooth), myLabels(1)
+    {
+        // today, then every payment date by repeated addition, then maturity (mcPrd.h:437-452)
+        myTimeline.push_back(systemTime);
+        for (Time t = systemTime + payFreq; myMaturity - t > ONE_DAY; t += payFreq) {
+            myDt.push_back(t - myTimeline.back());
+            myTimeline.push_back(t);
+        }
+        myDt.push_back(myMaturity - myTimeline.back());
+        myTimeline.push_back(myMaturity);
+
+        const size_t n = myTimeline.size();
+        myDefline.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            myDefline[i].forwardMats.push_back({myTimeline[i]});             // spot(T_i)
+            if (i + 1 < n) myDefline[i].liborDefs.push_back(SampleDef::RateDef(myTimeline[i], myTimeline[i + 1], "libor"));
+            myDefline[i].numeraire = i > 0;                                    // payments on every date but today
+        }
+        std::ostringstream ost;
+        ost.precision(2);
+        ost << std::fixed << "contingent bond " << myMaturity << " " << myCpn;
+        myLabels[0] = ost.str();
+    }
+
+    Time maturity() const { return myMaturity; }
+    double coupon() const { return myCpn; }
+    double smooth() const { return mySmooth; }
+    const std::vector<double>& coverages() const { return myDt; }
+
+    std::unique_ptr<Product<T>> clone() const override { return std::make_unique<ContingentBond<T>>(*this); }
+    const std::vector<Time>& timeline() const override { return myTimeline; }
+    const std::vector<SampleDef>& defline() const override { return myDefline; }
+    const std::vector<std::string>& payoffLabels() const override { return myLabels; }
+
+    bool deviceImage(ProductImage& img, const ModelImage& mdl) const override
+    {
+        // the half-width of the digital is a plain double of the FIRST sample's forward (mcPrd.h:531): today's
+        if (mdl.pod.n_assets != 1 || mdl.pod.kind != CF_MODEL_BS || !mdl.firstSampleIsToday) return false;
+        img = ProductImage();
+        img.pod.kind = CF_PRODUCT_CONTINGENT; img.pod.n_events = int(myTimeline.size()); img.pod.n_payoffs = 1;
+        img.pod.coupon = myCpn;
+        img.pod.smooth = double(mdl.firstSampleForward * mySmooth);
+        img.eventDt = myDt;
+        img.pod.event_dt = img.eventDt.data();
+        return true;
+    }
+};
+
 template <class T>
 class Europeans : public Product<T>
 {

@@ -81,6 +81,14 @@ inline void putBarrier(const double strike, const double barrier, const Time mat
     cfPutProduct<UOC>(store, strike, barrier, maturity, monitorFreq, smoothFactor, callPut);
 }
 
+// store.h:165-184 (note the argument order: coupon first)
+inline void putContingent(const double coupon, const Time maturity, const double payFreq, const double smooth,
+                          const std::string& store)
+{
+    const double smoothFactor = smooth <= 0 ? 0.0 : smooth;
+    cfPutProduct<ContingentBond>(store, maturity, coupon, payFreq, smoothFactor);
+}
+
 inline void putEuropeans(const std::vector<Time>& maturities /* increasing */, const std::vector<double>& strikes,
                          const std::string& store)
 {

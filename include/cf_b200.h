@@ -62,6 +62,8 @@ typedef struct cf_model {
     const double* numeraires;      /* [n_events] */
     const double* fwd_factors;     /* [n_events] */
     const double* discounts;       /* [n_events] */
+    const double* libors;          /* [n_events] first libor of each event date (ContingentBond: libor(T_e, T_e+1),
+                                      mcMdlBS.h:262-276); NULL = the Sample default 0 */
 
     /* Dupire tables, mcMdlDupire.h:195-217 */
     int32_t       n_knots;         /* spot knots of the local-vol surface */
@@ -97,7 +99,8 @@ enum { CF_PRODUCT_EUROPEAN = 0,   /* mcPrd.h:29  */
        CF_PRODUCT_EUROPEANS = 2,  /* mcPrd.h:290 */
        CF_PRODUCT_BASKETS = 3,    /* mcPrdMulti.h:181 */
        CF_PRODUCT_AUTOCALL = 4,   /* mcPrdMulti.h:289 */
-       CF_PRODUCT_MULTISTATS = 5  /* mcPrdMulti.h:11  */ };
+       CF_PRODUCT_MULTISTATS = 5, /* mcPrdMulti.h:11  */
+       CF_PRODUCT_CONTINGENT = 6  /* mcPrd.h:404 ContingentBond (Black-Scholes only) */ };
 
 typedef struct cf_product {
     int32_t kind;
@@ -107,13 +110,15 @@ typedef struct cf_product {
     double  strike;          /* European / UOC / Autocall */
     double  barrier;         /* UOC barrier, Autocall KO */
     double  smooth;          /* UOC: ABSOLUTE half-width double(S(t0) * smoothFactor), mcPrd.h:247;
-                                Autocall: max(smooth, EPS), mcPrdMulti.h:318 */
-    double  coupon;          /* Autocall */
+                                Autocall: max(smooth, EPS), mcPrdMulti.h:318;
+                                ContingentBond: ABSOLUTE half-width double(S(t0) * smoothFactor), mcPrd.h:531 */
+    double  coupon;          /* Autocall; ContingentBond */
     /* Europeans: strikes of event e are strikes[strike_offsets[e] .. strike_offsets[e+1]) */
     const int32_t* strike_offsets;  /* [n_events + 1] */
     const double*  strikes;         /* Europeans / Baskets */
     const double*  weights;         /* Baskets weights [n_assets]; Autocall refs [n_assets] */
-    const double*  event_dt;        /* Autocall: accrual period per event [n_events] */
+    const double*  event_dt;        /* Autocall: accrual period per event [n_events];
+                                       ContingentBond: coverage of the period STARTING at event e, [n_events - 1] */
 } cf_product;
 
 /* ------------------------------------------------------------------------------------------
@@ -127,7 +132,7 @@ const char* cf_last_error(void);
 uint64_t cf_launch_count(void);
 
 /* Number of doubles in the table-adjoint vector of (model, product):
- *   BS      : 1 (spot) + n_steps (drifts) + n_steps (stds) + 3 * n_events (numeraire, fwd factor, discount)
+ *   BS      : 1 (spot) + n_steps (drifts) + n_steps (stds) + 4 * n_events (numeraire, fwd factor, discount, libor)
  *   Dupire  : 1 (spot) + n_steps * n_knots (interp_vols, step-major), or, when the time map is
  *             given, 1 (spot) + n_knots * n_times (vols, spot-major)
  *   Displaced: spots [A] | alphas [A] | chol [A][A] (lower) | dyn_fwd [D][A] | drifts [D][A] | stds [D][A] |

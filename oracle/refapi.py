@@ -91,6 +91,10 @@ class RefLib:
         self._chk(self.lib.ref_put_european(C.c_double(strike), C.c_double(exercise), C.c_double(settlement),
                                             id_.encode()))
 
+    def put_contingent(self, coupon, maturity, pay_freq, smooth, id_):
+        self._chk(self.lib.ref_put_contingent(C.c_double(coupon), C.c_double(maturity), C.c_double(pay_freq),
+                                              C.c_double(smooth), id_.encode()))
+
     def put_barrier(self, strike, barrier, maturity, freq, smooth, call_put, id_):
         self._chk(self.lib.ref_put_barrier(C.c_double(strike), C.c_double(barrier), C.c_double(maturity),
                                            C.c_double(freq), C.c_double(smooth), C.c_int(int(call_put)),

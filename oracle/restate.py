@@ -385,7 +385,7 @@ class BSTables:
         pt = self.product_timeline
         sb = adj[0]
         db, stb = adj[1:1 + D], adj[1 + D:1 + 2 * D]
-        nb, fb, cb = adj[1 + 2 * D:1 + 2 * D + E], adj[1 + 2 * D + E:1 + 2 * D + 2 * E], adj[1 + 2 * D + 2 * E:]
+        nb, fb, cb = adj[1 + 2 * D:1 + 2 * D + E], adj[1 + 2 * D + E:1 + 2 * D + 2 * E], adj[1 + 2 * D + 2 * E:1 + 2 * D + 3 * E]
         vol_bar = float(np.sum(stb * np.sqrt(self.dt)) - self.vol * np.sum(db * self.dt))
         mu_bar = float(np.sum(db * self.dt))
         rate_bar, div_bar = mu_bar, -mu_bar

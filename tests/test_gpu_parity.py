@@ -113,6 +113,45 @@ def test_ragged_path_counts_vs_reference(cf, ref, n, sobol):
     assert np.max(np.abs(vega - rvega)) < 1e-8 * max(np.max(np.abs(rvega)), 1e-3)
 
 
+def test_live_path_regimes_vs_reference(cf, ref):
+    """The reverse kernel sweeps only the paths with a non-zero payoff adjoint (the reference's tape skips
+    zero-adjoint nodes, AADNode.h:76).  Regimes: many live paths per block (the European payoff carries weight:
+    several passes of 4 paths per thread), none at all (deep out of the money: every risk is exactly zero),
+    and everything in between on a shard that starts in the middle of the sequence."""
+    put_config3(cf, "dup3", "uoc3")
+    put_config3(ref, "dup3", "uoc3")
+    n = 1 << 19
+    val, delta, vega = cf.dupire_aad_risk("dup3", "uoc3", [0.3, 0.7], 30, 36, n)
+    rval, rdelta, rvega = ref.dupire_aad_risk("dup3", "uoc3", [0.3, 0.7], 30, 36, n)
+    assert abs(val / rval - 1) < PRICE_TOL and abs(delta / rdelta - 1) < RISK_TOL
+    check_vega(vega, rvega)
+    cf.put_barrier(400.0, 500.0, 3.0, 1.0 / 52, 0.01, False, "otm"); ref.put_barrier(400.0, 500.0, 3.0, 1.0 / 52, 0.01, False, "otm")
+    val, delta, vega = cf.dupire_aad_risk("dup3", "otm", [1.0, 1.0], 30, 36, 1 << 16)
+    rval, rdelta, rvega = ref.dupire_aad_risk("dup3", "otm", [1.0, 1.0], 30, 36, 1 << 16)
+    assert val == 0.0 and rval == 0.0 and delta == 0.0 and rdelta == 0.0
+    assert not np.any(vega) and not np.any(rvega)
+
+
+@pytest.mark.parametrize("sobol", [True, False])
+def test_contingent_bond_black_scholes(cf, ref, sobol):
+    """ContingentBond (mcPrd.h:404-574) under Black-Scholes: libors, numeraires on every payment date, a smoothed
+    digital on consecutive samples.  Value, per-path payoffs, AAD risks (spot, vol, rate, div) and bumps."""
+    cf.put_black_scholes(100, 0.2, False, 0.03, 0.01, "bsc"); ref.put_bs(100, 0.2, False, 0.03, 0.01, "bsc")
+    cf.put_contingent(0.02, 3.0, 0.25, 0.01, "cb"); ref.put_contingent(0.02, 3.0, 0.25, 0.01, "cb")
+    assert np.array_equal(cf.product_timeline("cb"), ref.product_timeline("cb")) and len(cf.product_timeline("cb")) == 13
+    n = 1 << 14
+    assert np.max(np.abs(cf.simul_paths("bsc", "cb", n, sobol=sobol) - ref.simul_paths("bsc", "cb", n, sobol=sobol))) < 1e-9
+    assert rel_err(cf.value("bsc", "cb", n, sobol=sobol), ref.value("bsc", "cb", n, sobol=sobol)) < PRICE_TOL
+    pv, v, risks = cf.aad_risk_one("bsc", "cb", n, sobol=sobol)
+    rpv, rv, rrisks = ref.aad_risk_one("bsc", "cb", n, sobol=sobol)
+    assert abs(v / rv - 1) < PRICE_TOL and rel_err(risks, rrisks) < RISK_TOL
+    # no smoothing: the digital has no fuzzy zone left, only the libor / numeraire chains carry risk
+    cf.put_contingent(0.05, 1.0, 0.5, 0.0, "cb0"); ref.put_contingent(0.05, 1.0, 0.5, 0.0, "cb0")
+    pv, v, risks = cf.aad_risk_one("bsc", "cb0", 4097, sobol=sobol)
+    rpv, rv, rrisks = ref.aad_risk_one("bsc", "cb0", 4097, sobol=sobol)
+    assert abs(v / rv - 1) < PRICE_TOL and np.max(np.abs(np.asarray(risks) - np.asarray(rrisks))) < 1e-8 * max(1.0, np.max(np.abs(rrisks)))
+
+
 def test_per_path_aad_results_vs_reference(cf, ref):
     """mcSimulAAD's per-path outputs (payoffs, aggregated) through the mirrored free function."""
     cf.put_black_scholes(100, 0.2, False, 0.02, 0.0, "bsx"); ref.put_bs(100, 0.2, False, 0.02, 0.0, "bsx")

@@ -53,7 +53,7 @@ def test_bs_tables_match_oracle(api):
     d = api.describe("bs", "eur", aad=True)
     assert (d["tab_a"] == tb.drifts).all() and (d["tab_b"] == tb.stds).all()
     assert d["numeraires"][0] == tb.numeraires[0] and d["fwd_factors"][0] == tb.fwd_factors[0]
-    assert d["discounts"][0] == tb.discounts[0] and d["adjoint_size"] == 1 + 2 + 3
+    assert d["discounts"][0] == tb.discounts[0] and d["adjoint_size"] == 1 + 2 + 4      # spot, drift, std, numeraire, fwd factor, discount, libor
     api.put_barrier(100, 120, 1.0, 1.0 / 52, 0.01, False, "uoc1y")
     ptl = R.uoc_timeline(1.0, 1.0 / 52)
     tb2 = R.BSTables(100, 0.15, 0.03, 0.01, ptl, ptl, [None] * len(ptl), [False] * (len(ptl) - 1) + [True])

@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
 
 HOST_DIR = os.path.join(HERE, "host")
 HOST_LIB = os.path.join(LIB_DIR, "libcf_host.so")
-HOST_DEPS = ["cf_export.cpp", "cf_main.h", "cf_store.h", "cf_products.h", "cf_products_multi.h", "cf_models.h", "cf_models_multi.h", "cf_rng.h", "cf_base.h",
+HOST_DEPS = ["cf_export.cpp", "cf_xl.h", "cf_xlcall.h", "cf_main.h", "cf_store.h", "cf_products.h", "cf_products_multi.h", "cf_models.h", "cf_models_multi.h", "cf_rng.h", "cf_base.h",
              "cf_aad.h", "cf_matrix.h", "cf_util.h", "cf_calib.h"]
 
 

@@ -383,3 +383,5 @@ int cfx_rng_sequence(int useSobol, int seed1, int seed2, int dim, unsigned skip,
 }
 
 }  // extern "C"
+
+#include "cf_xl.h"

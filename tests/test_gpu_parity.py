@@ -202,6 +202,21 @@ def test_shards_add_up(eng):
         assert np.max(np.abs(tot - whole["table_adj"])) < 1e-9 * np.max(np.abs(whole["table_adj"]))
 
 
+def test_runs_longer_than_one_launch_and_mid_size_shards(eng):
+    """A run of more than 2^21 paths is cut into launches that accumulate into the same per-warp tables; a mid-size
+    shard takes the 1-path-per-thread forward shape with every SM busy.  Both must add up to the same sums."""
+    tab, mdl, prd = _config3_lowlevel(eng)
+    w = [1.0, 0.5]
+    n = (1 << 21) + 4097
+    whole = eng.run_aad(mdl, prd, eng.rng("sobol"), 0, n, w)
+    cuts = [0, 100_000, 100_000 + (1 << 20), n]
+    parts = [eng.run_aad(mdl, prd, eng.rng("sobol"), a, b - a, w) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert abs(sum(p["agg_sum"] for p in parts) / whole["agg_sum"] - 1) < 1e-13
+    assert np.max(np.abs(sum(p["payoff_sums"] for p in parts) / whole["payoff_sums"] - 1)) < 1e-13
+    tot = sum(p["table_adj"] for p in parts)
+    assert np.max(np.abs(tot - whole["table_adj"])) < 1e-11 * np.max(np.abs(whole["table_adj"]))
+
+
 def test_generic_kernel_matches_fast_kernel(eng):
     tab, mdl_fast, prd = _config3_lowlevel(eng, True)
     _, mdl_gen, _ = _config3_lowlevel(eng, False)

@@ -17,6 +17,10 @@ import argparse
 import ctypes as C
 import json
 import os
+
+# rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it; set before torch loads NCCL
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 import subprocess
 import sys
 import threading
@@ -127,9 +131,6 @@ def run_reference(args):
 
 
 def main():
-    # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -178,9 +179,33 @@ def main():
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
+    # The sum over ranks is part of the final reduction kernel (peer memory over NVLink, cf_plan_set_peers); it is
+    # checked once against one NCCL all-reduce of the per-rank results, which is also the fallback.
+    fused = False
+    if world > 1:
+        try:
+            from compfinance_b200.dist import PeerSum
+            peer = PeerSum(n_out)
+            eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first, count, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
+            dist.all_reduce(d_out)
+            want = d_out.clone()
+            peer.attach(eng.lib, plan)
+            for _ in range(2):
+                eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first, count, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
+            torch.cuda.synchronize()
+            okf = torch.tensor([1.0 if torch.allclose(d_out, want, rtol=1e-11, atol=1e-9) else 0.0], device="cuda")
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            fused = bool(okf.item() > 0.5)
+            if not fused:
+                peer.detach(eng.lib, plan)
+        except Exception as ex:                                   # symmetric memory unavailable: NCCL per step
+            if rank == 0:
+                print(f"bench.py: peer-memory reduction unavailable ({type(ex).__name__}: {ex}); using NCCL", file=sys.stderr)
+            fused = False
+
     def step():
         eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first, count, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
-        if world > 1:
+        if world > 1 and not fused:
             dist.all_reduce(d_out)
 
     sampler = ClockSampler(local_rank)
@@ -283,7 +308,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "paths": N_PATHS, "steps_per_path": 156, "surface": "30x36", "rng": "sobol",
-                       "risks": 1081, "parallelism": f"paths sharded over {world} GPU(s), one NCCL all-reduce of {n_out} doubles",
+                       "risks": 1081, "parallelism": (f"paths sharded over {world} GPU(s), sum of {n_out} doubles over ranks inside the reduction kernel (peer memory over NVLink)" if fused else f"paths sharded over {world} GPU(s), one NCCL all-reduce of {n_out} doubles"),
                        "l2": "flushed between timed iterations (256 MB write)", "price": price, "delta": delta},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d,
                                       "d2h_bytes_per_step": d2h, "steps": e2e_steps,

@@ -65,6 +65,7 @@ def load():
     lib.cf_plan_launch_value.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.cf_plan_launch_aad.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.cf_plan_kernel_ms.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int)]
+    lib.cf_plan_set_peers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.cf_run_value.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product), C.POINTER(cf_rng), C.c_uint64,
                                  C.c_uint64, _dp, _dp]
     lib.cf_run_aad.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product), C.POINTER(cf_rng), C.c_uint64,
@@ -82,7 +83,7 @@ def load():
 EXPORTED = [
     "cf_init", "cf_shutdown", "cf_last_error", "cf_launch_count", "cf_table_adjoint_size", "cf_run_value",
     "cf_run_aad", "cf_run_aad_multi", "cf_plan_create", "cf_plan_destroy", "cf_plan_launch_value", "cf_plan_launch_aad",
-    "cf_plan_out_size", "cf_plan_kernel_ms", "cf_sobol_states", "cf_sobol_direction_number", "cf_sobol_max_dim",
+    "cf_plan_out_size", "cf_plan_kernel_ms", "cf_plan_set_peers", "cf_sobol_states", "cf_sobol_direction_number", "cf_sobol_max_dim",
     "cf_rng_draw", "cf_mrg_numerators", "cf_inv_normal", "cf_measure_fp64_peak", "cf_device_sm_count",
 ]
 

@@ -246,6 +246,9 @@ struct cf_plan {
     int D = 0, m = 0, E = 0, dim = 0, nPay = 0;
     size_t nAdj = 0;           // table adjoints including the spot leaf
     DevBuf<unsigned char> arena;      // one device block for all the tables uploaded by make_plan
+    cf::DPeers peers{};               // multi-GPU: the peers' result buffers and flags (cf_plan_set_peers), world = 0: none
+    uint32_t peerEpoch = 0;
+    DevBuf<uint32_t> peerTicket;
     bool tablesInFlight = true;       // the first launch orders its stream after the table upload (null stream)
     cf::KArgs base{};
     DevBuf<uint8_t> isEvent;
@@ -462,8 +465,15 @@ struct cf_plan {
         CF_CUDA(cudaEventRecord(ev.second, s));
         events.push_back(ev);
         const int nOut = int(outSize(aad));
+        cf::DPeers pr = peers;
+        if (pr.world > 1) {
+            if (pr.world > cf::kMaxPeers) throw CfError("cf_b200: too many peers");
+            pr.epoch = ++peerEpoch;
+            if (!peerTicket.p) { peerTicket.alloc(1); CF_CUDA(cudaMemsetAsync(peerTicket.p, 0, sizeof(uint32_t), s)); }
+            pr.ticket = peerTicket.p;
+        }
         cf::dupire_reduce_kernel<<<(nOut * 32 + 255) / 256, 256, 0, s>>>(g_scratch.partial.p, gridF, nPay, g_scratch.partialRev.p,
-                                                                        g_scratch.btab.p, gridR, m, nTimes, aad ? 1 : 0, dOut);
+                                                                        g_scratch.btab.p, gridR, m, nTimes, aad ? 1 : 0, dOut, pr);
         CF_CUDA(cudaGetLastError());
         ++g_launches;
     }
@@ -914,6 +924,24 @@ int cf_plan_launch_aad(cf_plan* plan, const double* payoff_weights, uint64_t fir
         if (!plan || !d_out || !payoff_weights) throw CfError("cf_plan_launch_aad: null argument");
         ensure_init();
         plan->launch(true, payoff_weights, first_path, n_paths, d_out, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int cf_plan_set_peers(cf_plan* plan, int world, int rank, void* const* peer_bufs, void* const* peer_flags)
+{
+    return guarded([&] {
+        if (!plan) throw CfError("cf_plan_set_peers: null plan");
+        if (world <= 1) { plan->peers = cf::DPeers{}; return; }
+        if (world > cf::kMaxPeers || rank < 0 || rank >= world || !peer_bufs || !peer_flags) throw CfError("cf_plan_set_peers: bad arguments");
+        if (!(plan->fast && plan->hasTimeMap)) throw CfError("cf_plan_set_peers: the fused reduction is part of the Dupire fast path only");
+        cf::DPeers p{};
+        p.world = world; p.rank = rank;
+        for (int r = 0; r < world; ++r) {
+            if (!peer_bufs[r] || !peer_flags[r]) throw CfError("cf_plan_set_peers: null peer pointer");
+            p.buf[r] = static_cast<double*>(peer_bufs[r]); p.flag[r] = static_cast<uint32_t*>(peer_flags[r]);
+        }
+        plan->peers = p;
+        plan->peerEpoch = 0;
     });
 }
 

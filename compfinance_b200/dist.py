@@ -34,3 +34,36 @@ def allreduce_sum_(t: torch.Tensor):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+class PeerSum:
+    """Exchange buffers of the fused reduce + all-reduce kernel (include/cf_b200.h: cf_plan_set_peers).
+
+    One symmetric allocation per rank -- [2][n_out] doubles for two alternating epochs, then `world` uint32 flag
+    words -- mapped into every process of the group by torch's symmetric memory (CUDA IPC / fabric handles over
+    NVLink).  The kernel does the rest: no collective is called per step.  Raises when symmetric memory is not
+    available (the caller falls back to one NCCL all-reduce per step)."""
+
+    def __init__(self, n_out: int):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        n_flag = (4 * self.world + 7) // 8 + 1
+        self.t = symm.empty(2 * n_out + n_flag, dtype=torch.float64, device="cuda")
+        self.t.zero_()
+        torch.cuda.synchronize()
+        self.handle = symm.rendezvous(self.t, dist.group.WORLD.group_name)
+        self.bufs = [int(p) for p in self.handle.buffer_ptrs]
+        self.flags = [p + 2 * n_out * 8 for p in self.bufs]
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def attach(self, lib, plan):
+        import ctypes as C
+        b = (C.c_void_p * self.world)(*self.bufs)
+        f = (C.c_void_p * self.world)(*self.flags)
+        rc = lib.cf_plan_set_peers(plan, self.world, self.rank, b, f)
+        if rc != 0:
+            raise RuntimeError(lib.cf_last_error().decode())
+
+    def detach(self, lib, plan):
+        lib.cf_plan_set_peers(plan, 0, 0, None, None)

@@ -204,6 +204,17 @@ int cf_inv_normal(const double* p, double* out, uint64_t n);
 
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU, paths sharded by [first_path, first_path + n_paths) per rank; mcBase.h has no
+ * counterpart: its workers share one address space and add their risks in mcBase.h:737-746).
+ * After this call the final reduction kernel of cf_plan_launch_aad / _value also sums over the ranks, through
+ * peer memory: peer_bufs[r] is rank r's exchange buffer (2 * cf_plan_out_size doubles) and peer_flags[r] its flag
+ * words (world uint32, zero-initialised), both mapped into this process (CUDA IPC / symmetric memory); every rank
+ * must then launch the same sequence of runs.  d_out receives the global sums, bit-identical on every rank.
+ * world <= 1 switches the exchange off.  Dupire fast path only.
+ * ---------------------------------------------------------------------------------------- */
+int cf_plan_set_peers(cf_plan* plan, int world, int rank, void* const* peer_bufs, void* const* peer_flags);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): scalar FP64 DFMA peak of the bound device in TFLOP/s
  * (2 flops per DFMA, 8 independent chains per thread, best of 4 timed launches) -- the roofline
  * denominator of this FP64-pipe-bound path; and the SM count.

@@ -18,9 +18,10 @@ import ctypes as C
 import json
 import os
 
-# rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it; set before torch loads NCCL
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# rank 0 prints ONE JSON line on stdout: NCCL writes its version banner there at NCCL_DEBUG=VERSION and =WARN
+# (init.cc showVersion); drop those two levels before torch loads NCCL (INFO / TRACE, if asked for, are kept)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    del os.environ["NCCL_DEBUG"]
 import subprocess
 import sys
 import threading
@@ -219,8 +220,12 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     evs = []
+    align = torch.zeros(1, device="cuda")
     for _ in range(args.steps):
         flush.fill_(1)                                           # L2 flush between timed iterations (untimed)
+        if world > 1:
+            dist.all_reduce(align)                               # untimed: the ranks' streams leave the flush together, so that
+                                                                 # a step is timed from a common start (max over ranks below)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step()
@@ -239,6 +244,12 @@ def main():
     value = N_PATHS / (ms_per_step * 1e-3)
     kms, kn = C.c_double(), C.c_int()
     eng._chk(eng.lib.cf_plan_kernel_ms(plan, C.byref(kms), C.byref(kn)))
+    kms_all = torch.tensor([kms.value], dtype=torch.float64, device="cuda")
+    if world > 1:
+        gathered = [torch.zeros_like(kms_all) for _ in range(world)]
+        dist.all_gather(gathered, kms_all)
+        kms_all = torch.cat(gathered)
+    kms_per_rank = [round(float(v), 5) for v in kms_all.cpu()]
     res = d_out.cpu().numpy()
     price, delta = res[2] / N_PATHS, res[3] / N_PATHS
 
@@ -288,7 +299,7 @@ def main():
         roofline = {
             "bound": "fp64", "kernel": "cf::dupire_forward4_kernel<UOC, AAD, Sobol, 2, 28> + cf::dupire_reverse_kernel<UOC> (one CUDA-event bracket around the pair)", "achieved": achieved, "peak": fp64_peak,
             "unit": "TFLOP/s", "frac": achieved / fp64_peak if achieved else None, "traffic": traffic,
-            "kernel_ms": kms.value, "kernel_launches_timed": kn.value,
+            "kernel_ms": kms.value, "kernel_ms_per_rank": kms_per_rank, "kernel_launches_timed": kn.value,
             "peak_source": "measured here: scalar DFMA microbenchmark cf_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 entry)",
             "algorithmic_flops_per_path": FLOPS_PER_PATH,
             "hbm": {"achieved_gbs": (traffic / (kms.value * 1e-3) / 1e9) if traffic and kms.value > 0 else None,
@@ -309,7 +320,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "paths": N_PATHS, "steps_per_path": 156, "surface": "30x36", "rng": "sobol",
                        "risks": 1081, "parallelism": (f"paths sharded over {world} GPU(s), sum of {n_out} doubles over ranks inside the reduction kernel (peer memory over NVLink)" if fused else f"paths sharded over {world} GPU(s), one NCCL all-reduce of {n_out} doubles"),
-                       "l2": "flushed between timed iterations (256 MB write)", "price": price, "delta": delta},
+                       "l2": "flushed between timed iterations (256 MB write)" + ("; ranks aligned by an untimed all-reduce after each flush" if world > 1 else ""), "price": price, "delta": delta},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d,
                                       "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                                       "api": "dupireAADRisk (libcf_host.so)" if world == 1 else "cf_run_aad (C ABI, host buffers) + NCCL all-reduce"},

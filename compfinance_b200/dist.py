@@ -39,7 +39,7 @@ def allreduce_sum_(t: torch.Tensor):
 class PeerSum:
     """Exchange buffers of the fused reduce + all-reduce kernel (include/cf_b200.h: cf_plan_set_peers).
 
-    One symmetric allocation per rank -- [2][n_out] doubles for two alternating epochs, then `world` uint32 flag
+    One symmetric allocation per rank -- [2][world][n_out] doubles (two alternating epochs, one row per sender), then `world` uint32 flag
     words -- mapped into every process of the group by torch's symmetric memory (CUDA IPC / fabric handles over
     NVLink).  The kernel does the rest: no collective is called per step.  Raises when symmetric memory is not
     available (the caller falls back to one NCCL all-reduce per step)."""
@@ -48,12 +48,12 @@ class PeerSum:
         import torch.distributed._symmetric_memory as symm
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         n_flag = (4 * self.world + 7) // 8 + 1
-        self.t = symm.empty(2 * n_out + n_flag, dtype=torch.float64, device="cuda")
+        self.t = symm.empty(2 * self.world * n_out + n_flag, dtype=torch.float64, device="cuda")
         self.t.zero_()
         torch.cuda.synchronize()
         self.handle = symm.rendezvous(self.t, dist.group.WORLD.group_name)
         self.bufs = [int(p) for p in self.handle.buffer_ptrs]
-        self.flags = [p + 2 * n_out * 8 for p in self.bufs]
+        self.flags = [p + 2 * self.world * n_out * 8 for p in self.bufs]
         dist.barrier()
         torch.cuda.synchronize()
 

@@ -207,7 +207,7 @@ int cf_inv_normal(const double* p, double* out, uint64_t n);
  * Multi-GPU (one process per GPU, paths sharded by [first_path, first_path + n_paths) per rank; mcBase.h has no
  * counterpart: its workers share one address space and add their risks in mcBase.h:737-746).
  * After this call the final reduction kernel of cf_plan_launch_aad / _value also sums over the ranks, through
- * peer memory: peer_bufs[r] is rank r's exchange buffer (2 * cf_plan_out_size doubles) and peer_flags[r] its flag
+ * peer memory: peer_bufs[r] is rank r's receive buffer (2 * world * cf_plan_out_size doubles) and peer_flags[r] its flag
  * words (world uint32, zero-initialised), both mapped into this process (CUDA IPC / symmetric memory); every rank
  * must then launch the same sequence of runs.  d_out receives the global sums, bit-identical on every rank.
  * world <= 1 switches the exchange off.  Dupire fast path only.

@@ -204,10 +204,36 @@ def main():
                 print(f"bench.py: peer-memory reduction unavailable ({type(ex).__name__}: {ex}); using NCCL", file=sys.stderr)
             fused = False
 
-    def step():
-        eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first, count, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
+    def step(first_path=first, n_paths=count):
+        eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first_path, n_paths, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
         if world > 1 and not fused:
             dist.all_reduce(d_out)
+
+    align = torch.zeros(1, device="cuda")
+
+    def timed(n_steps, first_path, n_paths):
+        """n_steps passes, each bracketed by CUDA events on the launching stream; returns ms per step, max over ranks."""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(n_steps):
+            flush.fill_(1)                                       # L2 flush between timed iterations (untimed)
+            if world > 1:
+                dist.all_reduce(align)                           # untimed: the ranks' streams leave the flush together, so that
+                                                                 # a step is timed from a common start (max over ranks below)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(first_path, n_paths)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n_steps
 
     sampler = ClockSampler(local_rank)
     sampler.start()                                              # nvidia-smi needs ~0.1 s to deliver its first sample
@@ -216,31 +242,8 @@ def main():
     torch.cuda.synchronize()
     eng._chk(eng.lib.cf_plan_kernel_ms(plan, None, None))       # drop warm-up kernel timings
     launches0 = eng.lib.cf_launch_count()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    evs = []
-    align = torch.zeros(1, device="cuda")
-    for _ in range(args.steps):
-        flush.fill_(1)                                           # L2 flush between timed iterations (untimed)
-        if world > 1:
-            dist.all_reduce(align)                               # untimed: the ranks' streams leave the flush together, so that
-                                                                 # a step is timed from a common start (max over ranks below)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        evs.append((e0, e1))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    ms_per_step = timed(args.steps, first, count)
     launches = eng.lib.cf_launch_count() - launches0
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
     value = N_PATHS / (ms_per_step * 1e-3)
     kms, kn = C.c_double(), C.c_int()
     eng._chk(eng.lib.cf_plan_kernel_ms(plan, C.byref(kms), C.byref(kn)))
@@ -252,6 +255,18 @@ def main():
     kms_per_rank = [round(float(v), 5) for v in kms_all.cpu()]
     res = d_out.cpu().numpy()
     price, delta = res[2] / N_PATHS, res[3] / N_PATHS
+
+    # ---- the same pass with 2^20 paths PER GPU (weak scaling), reported beside the strong-scaling headline
+    weak = None
+    if world > 1:
+        wfirst, wcount = shard_range(N_PATHS * world, rank, world)
+        for _ in range(args.warmup):
+            step(wfirst, wcount)
+        wms = timed(args.steps, wfirst, wcount)
+        eng._chk(eng.lib.cf_plan_kernel_ms(plan, None, None))
+        wres = d_out.cpu().numpy()
+        weak = {"paths_per_gpu": N_PATHS, "paths": N_PATHS * world, "ms_per_step": wms, "value": N_PATHS * world / (wms * 1e-3),
+                "unit": "paths/s", "price": wres[2] / (N_PATHS * world)}
 
     # ---- e2e: the call a user makes (dupireAADRisk through the host API, host buffers in and out)
     e2e_steps = max(3, min(args.steps, 10))
@@ -326,6 +341,8 @@ def main():
                                       "api": "dupireAADRisk (libcf_host.so)" if world == 1 else "cf_run_aad (C ABI, host buffers) + NCCL all-reduce"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
+        if weak:
+            line["weak_scaling"] = weak
         print(json.dumps(line))
     eng.lib.cf_plan_destroy(plan)
     if world > 1:

@@ -37,9 +37,8 @@ public:
 
     int record(int nArg, int a0, double d0, int a1 = -1, double d1 = 0.0)
     {
-        AADNode n;
+        AADNode& n = myNodes.emplace_back();
         n.nArg = nArg; n.arg[0] = a0; n.der[0] = d0; n.arg[1] = a1; n.der[1] = d1;
-        myNodes.push_back(n);
         return int(myNodes.size()) - 1;
     }
     AADNode& node(int i) { return myNodes[size_t(i)]; }
@@ -106,6 +105,9 @@ public:
 
     // result of a differentiable unary function evaluated outside this header (normalCdf, ...)
     static Number fromUnary(double v, const Number& a, double da) { return unary(v, a, da); }
+    // result of a differentiable binary expression recorded as ONE node, the way the reference's expression
+    // templates flatten an expression into a single multi-argument node (AADExpr.h:873-886)
+    static Number fromBinary(double v, const Number& a, double da, const Number& b, double db) { return binary(v, a, da, b, db); }
 
     Number() = default;
     Number(const double v) : myValue(v) {}

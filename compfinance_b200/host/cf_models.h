@@ -169,9 +169,11 @@ class Dupire : public Model<T>
     std::vector<Time> myTimeline;
     std::vector<bool> myCommonSteps;             // timeline point is an event date
     matrix<T>         myInterpVols;              // time major, already multiplied by sqrt(dt)
+    std::vector<int>    myCol1, myCol2;          // init(): interpVols[i][.] = w1[i] vols[.][col1[i]] + w2[i] vols[.][col2[i]]
+    std::vector<double> myW1, myW2;
 
     std::vector<T*>          myParameters;
-    std::vector<std::string> myParameterLabels;
+    std::shared_ptr<std::vector<std::string>> myParameterLabels;   // immutable after construction: shared by the clones
 
     void setParamPointers()
     {
@@ -184,16 +186,17 @@ public:
     Dupire(const U spot, const std::vector<double> spots, const std::vector<Time> times, const matrix<U> vols,
            const Time maxDt = 0.25)
         : mySpot(spot), mySpots(spots), myLogSpots(spots.size()), myTimes(times), myVols(vols), myMaxDt(maxDt),
-          myParameters(vols.rows() * vols.cols() + 1), myParameterLabels(vols.rows() * vols.cols() + 1)
+          myParameters(vols.rows() * vols.cols() + 1),
+          myParameterLabels(std::make_shared<std::vector<std::string>>(vols.rows() * vols.cols() + 1))
     {
         std::transform(mySpots.begin(), mySpots.end(), myLogSpots.begin(), [](const double s) { return std::log(s); });
-        myParameterLabels[0] = "spot";
+        (*myParameterLabels)[0] = "spot";
         size_t p = 0;
         for (size_t i = 0; i < myVols.rows(); ++i)
             for (size_t j = 0; j < myVols.cols(); ++j) {
                 std::ostringstream ost;
                 ost << std::setprecision(2) << std::fixed << "lvol " << mySpots[i] << " " << myTimes[j];
-                myParameterLabels[++p] = ost.str();
+                (*myParameterLabels)[++p] = ost.str();
             }
         setParamPointers();
     }
@@ -206,7 +209,7 @@ public:
     const std::vector<Time>& simulationTimeline() const { return myTimeline; }
 
     const std::vector<T*>& parameters() override { return myParameters; }
-    const std::vector<std::string>& parameterLabels() const override { return myParameterLabels; }
+    const std::vector<std::string>& parameterLabels() const override { return *myParameterLabels; }
 
     std::unique_ptr<Model<T>> clone() const override
     {
@@ -228,23 +231,81 @@ public:
 
     void init(const std::vector<Time>&, const std::vector<SampleDef>&) override
     {
-        // vols interpolated in time at the LEFT end of each step, times sqrt(dt) (mcMdlDupire.h:202-216)
-        const size_t n = myTimeline.size() - 1, m = myLogSpots.size();
+        // vols interpolated in time at the LEFT end of each step, times sqrt(dt) (mcMdlDupire.h:202-216).  The time
+        // bracket of a step is the same for every spot, so interp's upper_bound (interp.h:36-46) is done once per step;
+        // the arithmetic per entry is interp's, in its order.  On the host tape an entry is ONE node with its two
+        // parents (the flattened expression sqrtdt * (y1 + (y2 - y1) * t)), and the step's map
+        //   interpVols[i][j] = w1[i] vols[j][col1[i]] + w2[i] vols[j][col2[i]]
+        // is kept for deviceImage().
+        const size_t n = myTimeline.size() - 1, m = myLogSpots.size(), nT = myTimes.size();
+        myCol1.assign(n, 0); myCol2.assign(n, 0); myW1.assign(n, 0.0); myW2.assign(n, 0.0);
         for (size_t i = 0; i < n; ++i) {
             const double sqrtdt = std::sqrt(myTimeline[i + 1] - myTimeline[i]);
-            for (size_t j = 0; j < m; ++j)
-                myInterpVols[i][j] = sqrtdt * interp(myTimes.begin(), myTimes.end(), myVols[j], myVols[j] + myTimes.size(), myTimeline[i]);
+            const Time x0 = myTimeline[i];
+            const auto it = std::upper_bound(myTimes.begin(), myTimes.end(), x0);
+            if (it == myTimes.end() || it == myTimes.begin()) {         // flat extrapolation: a copy of the edge column
+                const size_t k = it == myTimes.end() ? nT - 1 : 0;
+                for (size_t j = 0; j < m; ++j) myInterpVols[i][j] = sqrtdt * myVols[j][k];
+                myCol1[i] = myCol2[i] = int(k); myW1[i] = sqrtdt; myW2[i] = 0.0;
+                continue;
+            }
+            const size_t k = size_t(std::distance(myTimes.begin(), it)) - 1;
+            const double t = (x0 - myTimes[k]) / (myTimes[k + 1] - myTimes[k]);
+            // derivatives as the sweep over sqrtdt * (y1 + (y2 - y1) * t) accumulates them; a zero weight is not a parent
+            const double w2 = sqrtdt * t, w1 = t != 0.0 ? sqrtdt + (-(sqrtdt * t)) : sqrtdt;
+            for (size_t j = 0; j < m; ++j) {
+                const T& y1 = myVols[j][k];
+                const T& y2 = myVols[j][k + 1];
+                if constexpr (std::is_same<T, Number>::value) {
+                    const double v = sqrtdt * (y1.value() + (y2.value() - y1.value()) * t);
+                    myInterpVols[i][j] = t != 0.0 ? Number::fromBinary(v, y1, w1, y2, w2) : Number::fromUnary(v, y1, w1);
+                } else
+                    myInterpVols[i][j] = sqrtdt * (y1 + (y2 - y1) * t);
+            }
+            myCol1[i] = int(k); myCol2[i] = t != 0.0 ? int(k + 1) : int(k); myW1[i] = w1; myW2[i] = t != 0.0 ? w2 : 0.0;
         }
     }
 
     size_t simDim() const override { return myTimeline.size() - 1; }
 
+    // The same map READ OFF THE TAPE of init() (leaf gradients of every table entry): true when every entry is a
+    // combination of at most two local vols of its own spot row, the same columns and weights along the row.
+    // Independent of what init() recorded; deviceImage() checks one against the other under CF_CHECK_TIME_MAP.
+    bool timeMapFromTape(ModelImage& img) const
+    {
+        if constexpr (!std::is_same<T, Number>::value) return false;
+        else {
+            const size_t D = myTimeline.size() - 1, m = myLogSpots.size(), nT = myTimes.size();
+            const Tape& tape = *Number::tape;
+            img.col1.assign(D, 0); img.col2.assign(D, 0); img.w1.assign(D, 0.0); img.w2.assign(D, 0.0);
+            std::vector<std::pair<int, double>> g;
+            for (size_t i = 0; i < D; ++i)
+                for (size_t j = 0; j < m; ++j) {
+                    g.clear();
+                    if (!myInterpVols[i][j].onTape()) return false;
+                    tape.leafGradient(myInterpVols[i][j].index(), 1.0, g);
+                    if (g.empty() || g.size() > 2) return false;
+                    int c[2] = {-1, -1}; double w[2] = {0.0, 0.0};
+                    for (size_t q = 0; q < g.size(); ++q) {
+                        // leaf must be one of vols[j][*]
+                        const int off = g[q].first - myVols[j][0].index();
+                        if (!myVols[j][0].onTape() || off < 0 || off >= int(nT) || myVols[j][off].index() != g[q].first) return false;
+                        c[q] = off; w[q] = g[q].second;
+                    }
+                    if (g.size() == 1) { c[1] = c[0]; w[1] = 0.0; }
+                    if (c[0] > c[1]) { std::swap(c[0], c[1]); std::swap(w[0], w[1]); }
+                    if (j == 0) { img.col1[i] = c[0]; img.col2[i] = c[1]; img.w1[i] = w[0]; img.w2[i] = w[1]; }
+                    else if (img.col1[i] != c[0] || img.col2[i] != c[1] || img.w1[i] != w[0] || img.w2[i] != w[1]) return false;
+                }
+            return true;
+        }
+    }
+
     // Device image.  Adjoint layout without the time map: [spot, interpVols[D][m]]; with it:
     // [spot, vols[m][nTimes]] (the parameter order).  For T = Number the time map
     //   interpVols[i][j] = w1[i] vols[j][col1[i]] + w2[i] vols[j][col2[i]]
-    // is READ OFF THE TAPE of init() (leaf gradients of every table entry) and only used when every
-    // entry has exactly that structure; otherwise the table adjoints come back and the tape sweep
-    // mark -> start does the chain rule.
+    // is the one init() recorded, used when the spot and every local vol are on tape; otherwise the table
+    // adjoints come back and the tape sweep mark -> start does the chain rule.
     bool deviceImage(ModelImage& img, const std::vector<Time>& productTimeline, const std::vector<SampleDef>& defline) override
     {
         const size_t D = myTimeline.size() - 1, m = myLogSpots.size(), E = productTimeline.size(), nT = myTimes.size();
@@ -265,30 +326,15 @@ public:
         img.firstSampleIsToday = myCommonSteps[0];
         img.firstSampleForward = std::exp(std::log(cfValue(mySpot)));      // exp(logspot), mcMdlDupire.h:252
         if constexpr (std::is_same<T, Number>::value) {
-            const Tape& tape = *Number::tape;
-            bool structured = mySpot.onTape();
-            img.col1.assign(D, 0); img.col2.assign(D, 0); img.w1.assign(D, 0.0); img.w2.assign(D, 0.0);
-            std::vector<std::pair<int, double>> g;
-            for (size_t i = 0; i < D && structured; ++i) {
-                for (size_t j = 0; j < m && structured; ++j) {
-                    g.clear();
-                    if (!myInterpVols[i][j].onTape()) { structured = false; break; }
-                    tape.leafGradient(myInterpVols[i][j].index(), 1.0, g);
-                    if (g.empty() || g.size() > 2) { structured = false; break; }
-                    int c[2] = {-1, -1}; double w[2] = {0.0, 0.0};
-                    for (size_t q = 0; q < g.size(); ++q) {
-                        // leaf must be one of vols[j][*]
-                        const int base = myVols[j][0].index();
-                        const int off = g[q].first - base;
-                        if (!myVols[j][0].onTape() || off < 0 || off >= int(nT) || myVols[j][off].index() != g[q].first) { structured = false; break; }
-                        c[q] = off; w[q] = g[q].second;
-                    }
-                    if (!structured) break;
-                    if (g.size() == 1) { c[1] = c[0]; w[1] = 0.0; }
-                    if (c[0] > c[1]) { std::swap(c[0], c[1]); std::swap(w[0], w[1]); }
-                    if (j == 0) { img.col1[i] = c[0]; img.col2[i] = c[1]; img.w1[i] = w[0]; img.w2[i] = w[1]; }
-                    else if (img.col1[i] != c[0] || img.col2[i] != c[1] || img.w1[i] != w[0] || img.w2[i] != w[1]) structured = false;
-                }
+            // the map recorded by init(); usable when the spot and every local vol are leaves of the tape
+            bool structured = mySpot.onTape() && myCol1.size() == D
+                              && std::all_of(myVols.begin(), myVols.end(), [](const Number& v) { return v.onTape(); });
+            img.col1 = myCol1; img.col2 = myCol2; img.w1 = myW1; img.w2 = myW2;
+            static const bool check = std::getenv("CF_CHECK_TIME_MAP") != nullptr;
+            if (structured && check) {
+                ModelImage ref;
+                if (!timeMapFromTape(ref) || ref.col1 != img.col1 || ref.col2 != img.col2 || ref.w1 != img.w1 || ref.w2 != img.w2)
+                    throw std::runtime_error("Dupire::deviceImage: init()'s time map differs from the one read off the tape");
             }
             auto& t = img.adjointTargets;
             if (structured) {

@@ -97,3 +97,38 @@ def test_dupire_calibration_matches_reference(api, ref):
     s_r, t_r, lv_r = ref.dupire_calib(*args)
     assert np.array_equal(s, s_r) and np.array_equal(t, t_r)
     assert lv.shape == lv_r.shape and np.max(np.abs(lv / lv_r - 1)) < 1e-12
+
+
+def test_time_map_recorded_by_init_equals_the_one_read_off_the_tape(built):
+    """Dupire::init() records the step -> (two time columns, weights) map itself; under CF_CHECK_TIME_MAP
+    deviceImage() also derives it from the leaf gradients of the tape and throws on any difference.  Cases:
+    config 3, a surface whose time knots coincide with simulation dates (t == 0: one parent only) and one
+    whose knots start after today and end before maturity (flat extrapolation on both sides)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np
+from compfinance_b200.api import CompFinance
+cf = CompFinance()
+spots = np.arange(55, 201, 5.0)
+cases = {"cfg3": np.arange(1, 37) / 12.0, "on_dates": np.arange(0, 13) * 0.25, "flat_both": np.array([0.6, 1.1, 1.9])}
+cf.put_barrier(120.0, 150.0, 3.0, 1.0 / 52, 0.01, False, "uoc")
+cf.put_european(110.0, 2.0, 2.0, "eur")
+for name, times in cases.items():
+    vols = 0.15 + 0.10 * np.log(spots[:, None] / 100.0) ** 2 + 0.02 * times[None, :]
+    cf.put_dupire(100.0, spots, times, vols, 0.25, name)
+    for prd in ("uoc", "eur"):
+        d = cf.describe(name, prd, aad=True)
+        assert d["n_times"] == times.size and d["adjoint_size"] == 1 + spots.size * times.size, (name, prd)
+        nT, c1, c2, w1, w2 = d["time_map"]
+        assert (c1 <= c2).all() and (w2[c1 == c2] == 0).all()
+        # the map reproduces the table: interpVols[i][j] = w1 vols[j][c1] + w2 vols[j][c2]
+        rebuilt = w1[:, None] * vols[:, c1].T + w2[:, None] * vols[:, c2].T
+        assert np.max(np.abs(rebuilt - d["tab_a"])) < 1e-15, (name, prd)
+print("ok")
+'''
+    env = dict(os.environ, CF_CHECK_TIME_MAP="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

@@ -13,7 +13,10 @@ COMMON = ["cf_device.cuh", "cf_kernels.cuh", "cf_pick.h", os.path.join("..", "..
 UNITS = {
     "cf_api.cu": ["cf_tables.h", "cf_dupire.cuh", "cf_dlm.cuh", "cf_multi.cuh"],
     "cf_pick_path.cu": ["cf_multi.cuh"],
-    "cf_pick_dlm.cu": ["cf_dlm.cuh"],
+    "cf_pick_dlm.cu@4": ["cf_dlm.cuh"],      # one unit per asset-count bucket: -DCF_DLM_AMAX=<n>
+    "cf_pick_dlm.cu@8": ["cf_dlm.cuh"],
+    "cf_pick_dlm.cu@12": ["cf_dlm.cuh"],
+    "cf_pick_dlm.cu@16": ["cf_dlm.cuh"],
     "cf_pick_dupire.cu": ["cf_dupire.cuh"],
     "cf_tables.cpp": ["cf_tables.h", "joe_kuo_init.inc"],
 }
@@ -27,12 +30,20 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _src(unit):
+    return unit.split("@")[0]
+
+
+def _defines(unit):
+    return ["-DCF_DLM_AMAX=" + unit.split("@")[1]] if "@" in unit else []
+
+
 def _obj(unit):
-    return os.path.join(OBJ_DIR, os.path.splitext(unit)[0] + ".o")
+    return os.path.join(OBJ_DIR, os.path.splitext(_src(unit))[0] + ("_" + unit.split("@")[1] if "@" in unit else "") + ".o")
 
 
 def _deps(unit):
-    return [os.path.join(CSRC, d) for d in [unit] + UNITS[unit] + COMMON]
+    return [os.path.join(CSRC, d) for d in [_src(unit)] + UNITS[unit] + COMMON]
 
 
 def needs_build():
@@ -50,7 +61,7 @@ def build(force=False, verbose=False):
     def compile_unit(unit):
         if not force and not _stale(_obj(unit), _deps(unit)):
             return
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, unit), "-o", _obj(unit)]
+        cmd = [nvcc] + NVCC_FLAGS + _defines(unit) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, _src(unit)), "-o", _obj(unit)]
         print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
 

@@ -377,7 +377,7 @@ struct cf_plan {
         LKernel fn = cf::pick_dlm_kernel(A, prdKind, aad, rngKind);
         if (!fn) throw CfError("cf_b200: MultiStats is a value-only test instrument on the device (no AAD)");
         const size_t smem = cf::dlm_smem(A, D, E, nPay, dim, rngKind == CF_RNG_SOBOL, aad).total;
-        if (smem > kFastSmemLimit / 2) throw CfError("cf_b200: displaced model tables do not fit in shared memory (n_steps * n_assets or payoffs too large)");
+        if (smem > kFastSmemLimit) throw CfError("cf_b200: displaced model tables do not fit in shared memory (n_steps * n_assets or payoffs too large)");
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         auto ev = takeEvents();
         CF_CUDA(cudaEventRecord(ev.first, s));

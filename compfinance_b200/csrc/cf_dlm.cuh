@@ -8,9 +8,14 @@
 // (step-major dimension i * A + k), correlates them with the lower Cholesky factor, and advances
 // every asset with one of the four schemes.  The reverse sweep reads the spots, the Gaussians and
 // the alive notional back from a per-thread history ([row][slot], coalesced) and accumulates the
-// adjoints of every init() table: per-step tables through warp sums into per-warp shared-memory
-// rows, per-asset tables (spots, alphas, Cholesky) in thread-local accumulators reduced once at the
-// end.  All orders are fixed by lane / warp / block index: results are bit-reproducible.
+// adjoints of every init() table.  Sums over the 32 paths of a warp go through a per-warp scratch
+// block of rows [value][lane]: every lane writes its values, then lane r adds row r over the 32
+// columns from a rotated start (conflict free, fixed order) -- one pass for the 3 A per-step table
+// adjoints of a step instead of one shuffle tree per value.  The Cholesky adjoint
+// cholBar[k][j] = sum over paths and steps of cwBar_k w_j is an outer product over the same rows:
+// lane p owns the pairs p, p + 32, ... and keeps their sums in registers over the whole run.  Spot
+// and alpha adjoints are thread-local and reduced once at the end.  All orders are fixed by lane /
+// warp / block index: results are bit-reproducible.
 #pragma once
 
 #include "cf_kernels.cuh"
@@ -54,7 +59,7 @@ struct LArgs {
 __host__ __device__ inline int dlm_adj_size(int A, int D, int E) { return 2 * A + A * A + 3 * D * A + E + E * A; }
 __host__ __device__ inline int dlm_step_tables(int A, int D, int E) { return 3 * D * A + E + E * A; }
 
-struct LSmemSizes { size_t pay, tab, red, gq, tagq, dirlow, base, total; };
+struct LSmemSizes { size_t pay, tab, red, gq, tagq, dirlow, base, scr, total; };
 
 __host__ __device__ inline LSmemSizes dlm_smem(int A, int D, int E, int nPay, int dim, bool sobol, bool aad)
 {
@@ -66,12 +71,30 @@ __host__ __device__ inline LSmemSizes dlm_smem(int A, int D, int E, int nPay, in
     s.tagq = align16(sizeof(uint16_t) * kWarps * kChunk * 32);
     s.dirlow = sobol ? align16(sizeof(uint32_t) * size_t(dim) * kLowBits) : 0;
     s.base = sobol ? align16(sizeof(uint32_t) * 2 * size_t(dim)) : 0;
-    s.total = s.pay + s.tab + s.red + s.gq + s.tagq + s.dirlow + s.base;
+    s.scr = aad ? align16(sizeof(double) * kWarps * size_t(3 * A) * 32) : 0;     // per warp: [3 A][32] rows
+    s.total = s.pay + s.tab + s.red + s.gq + s.tagq + s.dirlow + s.base + s.scr;
     return s;
 }
 
+// Sum of one scratch row (32 doubles, one per lane of the warp that wrote it) from a rotated start: the lanes of
+// a half-warp read 16 different 8-byte banks.  Four partial sums, fixed order.
+__device__ __forceinline__ double dlm_row_sum(const double* row, int lane)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+        s0 += row[(lane + c) & 31]; s1 += row[(lane + c + 1) & 31];
+        s2 += row[(lane + c + 2) & 31]; s3 += row[(lane + c + 3) & 31];
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// Rounds of 32 (k, j <= k) pairs of the Cholesky adjoint owned by a lane
+template <int AMAX> struct DlmPairs { static constexpr int kRounds = (AMAX * (AMAX + 1) / 2 + 31) / 32; };
+
+// AAD with more than 8 assets: one block per SM (up to 255 registers: spot, Gaussian and adjoint vectors stay in registers)
 template <int AMAX, int PRD, bool AAD, int RNGK>
-__global__ void __launch_bounds__(kBlock, 2) dlm_kernel(const LArgs a)
+__global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(const LArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -85,7 +108,8 @@ __global__ void __launch_bounds__(kBlock, 2) dlm_kernel(const LArgs a)
     double* gq = reinterpret_cast<double*>(p);          p += z.gq;
     uint16_t* tagq = reinterpret_cast<uint16_t*>(p);    p += z.tagq;
     uint32_t* dirlow = reinterpret_cast<uint32_t*>(p);  p += z.dirlow;
-    uint32_t* base = reinterpret_cast<uint32_t*>(p);
+    uint32_t* base = reinterpret_cast<uint32_t*>(p);    p += z.base;
+    double* scrAll = reinterpret_cast<double*>(p);                        // [kWarps][3 A][32] (AAD)
 
     const int nPay = a.n_payoffs;
     const int nStepTab = dlm_step_tables(A, D, E);
@@ -108,12 +132,23 @@ __global__ void __launch_bounds__(kBlock, 2) dlm_kernel(const LArgs a)
     const int hRows = 2 * A + 1;                       // per step: spots after the step [A], Gaussians [A], alive before the event
     double aggSum = 0.0;
     // per-asset table adjoints, thread-local over all paths of the thread
-    double spotBar[AMAX], alphaBar[AMAX], cholBar[AMAX * (AMAX + 1) / 2];
+    double spotBar[AMAX], alphaBar[AMAX];
+    // Cholesky adjoint: pair p = k (k + 1) / 2 + j of round q is owned by lane p - 32 q of every warp
+    constexpr int kRounds = DlmPairs<AMAX>::kRounds;
+    double cholAcc[kRounds];
+    int pairK[kRounds], pairJ[kRounds];
+    double* scr = scrAll + size_t(warp) * (3 * A) * 32;
     if (AAD) {
 #pragma unroll
         for (int k = 0; k < AMAX; ++k) { spotBar[k] = 0.0; alphaBar[k] = 0.0; }
 #pragma unroll
-        for (int k = 0; k < AMAX * (AMAX + 1) / 2; ++k) cholBar[k] = 0.0;
+        for (int q = 0; q < kRounds; ++q) {
+            const int pp = lane + 32 * q;
+            int k = 0;
+            while ((k + 1) * (k + 2) / 2 <= pp) ++k;
+            pairK[q] = k; pairJ[q] = pp - k * (k + 1) / 2;      // k >= A: no such pair
+            cholAcc[q] = 0.0;
+        }
     }
     const double sm2 = 2.0 * a.smooth;
 
@@ -287,25 +322,32 @@ __global__ void __launch_bounds__(kBlock, 2) dlm_kernel(const LArgs a)
                     for (int k = 0; k < AMAX; ++k) if (k < A) Fbar[k] = bbar * __ldg(a.pweights + k);
                 }
                 // forwards[a][0] = spot * ff (fillScen, mcMdlMultiDisplaced.h:628-640)
-                double s = warp_sum(valid ? numbar : 0.0);
-                if (lane == 0 && a.num) myTab[oNum + ev] += s;
+                // rows 0 .. A - 1: forward-factor adjoints, row A: numeraire adjoint
 #pragma unroll
                 for (int k = 0; k < AMAX; ++k) {
                     if (k < A) {
-                        s = warp_sum(valid ? Fbar[k] * Sev[k] : 0.0);
-                        if (lane == 0) myTab[oFf + ev * A + k] += s;
+                        scr[k * 32 + lane] = valid ? Fbar[k] * Sev[k] : 0.0;
                         Sbar[k] += Fbar[k] * __ldg(a.ff + ev * A + k);
                     }
                 }
+                scr[A * 32 + lane] = valid ? numbar : 0.0;
+                __syncwarp();
+                if (lane <= A) {
+                    const double s = dlm_row_sum(scr + lane * 32, lane);
+                    if (lane < A) myTab[oFf + ev * A + lane] += s;
+                    else if (a.num) myTab[oNum + ev] += s;
+                }
+                __syncwarp();
             };
 
             int er = E - 1;
             for (int i = D - 1; i >= 0; --i) {
                 const double* h = a.hist + (size_t(i) * hRows) * nSlots + slot;
                 const double* hPrev = a.hist + (size_t(i > 0 ? i - 1 : 0) * hRows) * nSlots + slot;
-                double Sn[AMAX], Sp[AMAX], w[AMAX];
+                double Sn[AMAX], Sp[AMAX], w[AMAX], cwb[AMAX];
 #pragma unroll
                 for (int k = 0; k < AMAX; ++k) {
+                    cwb[k] = 0.0;
                     Sn[k] = (k < A) ? h[size_t(k) * nSlots] : 0.0;
                     w[k] = (k < A) ? h[size_t(A + k) * nSlots] : 0.0;
                     Sp[k] = (k < A) ? (i > 0 ? hPrev[size_t(k) * nSlots] : __ldg(a.spots + k)) : 0.0;
@@ -336,17 +378,41 @@ __global__ void __launch_bounds__(kBlock, 2) dlm_kernel(const LArgs a)
                             else { xbar = sb * (Sn[k] - al); alphaBar[k] += sb * (1.0 - ex); }                 // S = (fwd - al) e + al
                             sdbar = xbar * cw; cwbar = xbar * sd;
                         }
-                        double s = warp_sum(fwdbar * Sp[k]);
-                        if (lane == 0) myTab[oFwd + i * A + k] += s;
-                        s = warp_sum(xbar);
-                        if (lane == 0) myTab[oDrift + i * A + k] += s;
-                        s = warp_sum(sdbar);
-                        if (lane == 0) myTab[oStd + i * A + k] += s;
-#pragma unroll
-                        for (int j = 0; j <= k; ++j) cholBar[k * (k + 1) / 2 + j] += cwbar * w[j];
+                        // rows [0, A): dynFwd adjoints, [A, 2 A): drift adjoints, [2 A, 3 A): std adjoints
+                        scr[k * 32 + lane] = fwdbar * Sp[k];
+                        scr[(A + k) * 32 + lane] = xbar;
+                        scr[(2 * A + k) * 32 + lane] = sdbar;
+                        cwb[k] = cwbar;
                         Sbar[k] = fwdbar * df;
                     }
                 }
+                __syncwarp();
+                for (int r = lane; r < 3 * A; r += 32) {
+                    const int t = r / A;
+                    myTab[(t == 0 ? oFwd : t == 1 ? oDrift : oStd) + i * A + (r - t * A)] += dlm_row_sum(scr + r * 32, lane);
+                }
+                __syncwarp();
+                // outer product cwBar (x) w over the warp's paths: rows [0, A) = cwBar, [A, 2 A) = w
+#pragma unroll
+                for (int k = 0; k < AMAX; ++k)
+                    if (k < A) { scr[k * 32 + lane] = cwb[k]; scr[(A + k) * 32 + lane] = w[k]; }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < kRounds; ++q) {
+                    if (pairK[q] < A) {
+                        const double* xr = scr + pairK[q] * 32;
+                        const double* wr = scr + (A + pairJ[q]) * 32;
+                        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2) {
+                            const int c0 = (lane + c) & 31, c1 = (lane + c + 1) & 31;
+                            s0 = fma(xr[c0], wr[c0], s0);
+                            s1 = fma(xr[c1], wr[c1], s1);
+                        }
+                        cholAcc[q] += s0 + s1;
+                    }
+                }
+                __syncwarp();
             }
             if (a.today) {
                 double S0[AMAX];
@@ -381,16 +447,19 @@ __global__ void __launch_bounds__(kBlock, 2) dlm_kernel(const LArgs a)
             }
         }
         for (int k = tid; k < A * A; k += kBlock) adj[2 * A + k] = 0.0;
+        // Cholesky adjoint: the warps' pair sums through the (now idle) scratch rows, combined in warp order
+        const int nPairs = A * (A + 1) / 2, scrStride = 3 * A * 32;
+#pragma unroll
+        for (int q = 0; q < kRounds; ++q)
+            if (pairK[q] < A) scr[lane + 32 * q] = cholAcc[q];
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < AMAX; ++k)
-#pragma unroll
-            for (int j = 0; j <= k; ++j) {
-                if (k < A) {
-                    s = block_sum(cholBar[k * (k + 1) / 2 + j], red);
-                    if (tid == 0) adj[2 * A + k * A + j] = s;
-                }
-            }
+        for (int pp = tid; pp < nPairs; pp += kBlock) {
+            double t = 0.0;
+            for (int w = 0; w < kWarps; ++w) t += scrAll[size_t(w) * scrStride + pp];
+            int k = 0;
+            while ((k + 1) * (k + 2) / 2 <= pp) ++k;
+            adj[2 * A + k * A + (pp - k * (k + 1) / 2)] = t;
+        }
         __syncthreads();
         for (int k = tid; k < nStepTab; k += kBlock) {
             double t = 0.0;

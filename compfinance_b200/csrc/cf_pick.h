@@ -14,8 +14,8 @@ using MKernel = void (*)(const MArgs);
 KernelFn pick_path_kernel(int mdl, int prd, bool aad, int rng);
 // cf_pick_path.cu: itemised risk of Dupire x Europeans
 MKernel pick_multi_kernel(int rng);
-// cf_pick_dlm.cu: displaced multi-asset model; amax 4 or 16; nullptr: MultiStats with AAD
-LKernel pick_dlm_kernel(int amax, int prd, bool aad, int rng);
+// cf_pick_dlm.cu: displaced multi-asset model, instantiated for up to 4 / 8 / 12 / 16 assets; nullptr: MultiStats with AAD
+LKernel pick_dlm_kernel(int n_assets, int prd, bool aad, int rng);
 // cf_pick_dupire.cu: the north-star kernels; fwdP = paths per thread of the forward kernel, 1 or 2 (kFwdWarps warps per block)
 DKernel pick_dupire_forward(int prd, bool aad, int rng, int fwdP);
 DKernel pick_dupire_reverse(int prd);

@@ -1,6 +1,11 @@
-// Instantiations of the displaced multi-asset kernel (see cf_pick.h).
+// Instantiations of the displaced multi-asset kernel (see cf_pick.h).  One translation unit per asset-count bucket
+// (CF_DLM_AMAX = 4, 8, 12, 16, set by the build), compiled in parallel; the unit of bucket 4 also holds the dispatcher.
 #include "cf_dlm.cuh"
 #include "cf_pick.h"
+
+#ifndef CF_DLM_AMAX
+#error "CF_DLM_AMAX must be 4, 8, 12 or 16"
+#endif
 
 namespace cf {
 namespace {
@@ -22,8 +27,25 @@ LKernel pick1(int prd, bool aad, int rng)
 }
 }  // namespace
 
-LKernel pick_dlm_kernel(int amax, int prd, bool aad, int rng)
+LKernel pick_dlm_kernel_4(int prd, bool aad, int rng);
+LKernel pick_dlm_kernel_8(int prd, bool aad, int rng);
+LKernel pick_dlm_kernel_12(int prd, bool aad, int rng);
+LKernel pick_dlm_kernel_16(int prd, bool aad, int rng);
+
+#if CF_DLM_AMAX == 4
+LKernel pick_dlm_kernel_4(int prd, bool aad, int rng) { return pick1<4>(prd, aad, rng); }
+LKernel pick_dlm_kernel(int n_assets, int prd, bool aad, int rng)
 {
-    return amax <= 4 ? pick1<4>(prd, aad, rng) : pick1<16>(prd, aad, rng);
+    if (n_assets <= 4) return pick_dlm_kernel_4(prd, aad, rng);
+    if (n_assets <= 8) return pick_dlm_kernel_8(prd, aad, rng);
+    if (n_assets <= 12) return pick_dlm_kernel_12(prd, aad, rng);
+    return pick_dlm_kernel_16(prd, aad, rng);
 }
+#elif CF_DLM_AMAX == 8
+LKernel pick_dlm_kernel_8(int prd, bool aad, int rng) { return pick1<8>(prd, aad, rng); }
+#elif CF_DLM_AMAX == 12
+LKernel pick_dlm_kernel_12(int prd, bool aad, int rng) { return pick1<12>(prd, aad, rng); }
+#else
+LKernel pick_dlm_kernel_16(int prd, bool aad, int rng) { return pick1<16>(prd, aad, rng); }
+#endif
 }  // namespace cf

@@ -161,15 +161,22 @@ struct MrgThread {
         y0 = uint32_t(Y[0]); y1 = uint32_t(Y[1]); y2 = uint32_t(Y[2]);
     }
 
-    // next integer numerator z in [0, m1): u = z / (m1 + 1)
+    // next integer numerator z in [0, m1): u = z / (m1 + 1).  One reduction per component: the negative term is taken
+    // as a13 (m - x), so p = a12 x1 + a13 (m1 - x2) < 2^54 is non-negative and congruent; 2^32 = 209 (mod m1) and
+    // 22853 (mod m2) fold the high word twice, then one conditional subtraction.
     __device__ __forceinline__ uint32_t next()
     {
-        // a12 * Xn1 + (m1 - a13) * Xn2  < 2^21*2^32 + 2^32*2^32 -> fits uint64 (max ~1.8e19 < 1.84e19)
-        const uint64_t x = mod_m1(1403580ull * x1 + mod_m1((kM1 - 810728ull) * x2));
-        x2 = x1; x1 = x0; x0 = uint32_t(x);
-        const uint64_t y = mod_m2(527612ull * y0 + mod_m2((kM2 - 1370589ull) * y2));
-        y2 = y1; y1 = y0; y0 = uint32_t(y);
-        return x > y ? uint32_t(x - y) : uint32_t(x + kM1 - y);
+        const uint64_t px = 1403580ull * x1 + 810728ull * uint64_t(uint32_t(kM1) - x2);
+        uint64_t tx = uint64_t(uint32_t(px)) + uint64_t(uint32_t(px >> 32) * 209u);            // high word < 2^22: < 2^33
+        tx = uint64_t(uint32_t(tx)) + uint64_t(uint32_t(tx >> 32) * 209u);                    // < 2^32 + 209
+        const uint32_t x = uint32_t(tx >= kM1 ? tx - kM1 : tx);
+        x2 = x1; x1 = x0; x0 = x;
+        const uint64_t py = 527612ull * y0 + 1370589ull * uint64_t(uint32_t(kM2) - y2);
+        uint64_t ty = uint64_t(uint32_t(py)) + uint64_t(uint32_t(py >> 32)) * 22853ull;         // < 2^38
+        ty = uint64_t(uint32_t(ty)) + uint64_t(uint32_t(ty >> 32) * 22853u);                  // < 2^32 + 2^21
+        const uint32_t y = uint32_t(ty >= kM2 ? ty - kM2 : ty);
+        y2 = y1; y1 = y0; y0 = y;
+        return x > y ? x - y : uint32_t(uint64_t(x) + kM1 - y);
     }
 };
 

@@ -307,8 +307,9 @@ __global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(
                         numbar = -paybar * (aliveBefore * a.coupon * a.cpn_dt + aliveBefore - aliveBefore * put / a.strike) / (num * num);
                         alivebar = paybar * (a.coupon * a.cpn_dt / num + 1.0 / num - put / a.strike / num);
                     }
+                    const double fb = worstbar / __ldg(a.pweights + am);      // one division: only the worst performer carries the adjoint
 #pragma unroll
-                    for (int k = 0; k < AMAX; ++k) if (k == am) Fbar[k] = worstbar / __ldg(a.pweights + k);
+                    for (int k = 0; k < AMAX; ++k) if (k == am) Fbar[k] = fb;
                 } else if (PRD == CF_PRODUCT_BASKETS) {
                     double b = 0.0;
 #pragma unroll

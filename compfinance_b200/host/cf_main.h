@@ -92,6 +92,20 @@ inline AADRiskResults AADriskOne(const std::string& modelId, const std::string& 
     return cfAADrisk(*model, *product, weights, num);
 }
 
+// Notionals by payoff label -> weight vector in payoff order (main.h:196-207)
+inline std::vector<double> cfNotionalWeights(const Product<Number>& product, const std::map<std::string, double>& notionals,
+                                             const char* who)
+{
+    const std::vector<std::string>& allPayoffs = product.payoffLabels();
+    std::vector<double> vnots(allPayoffs.size(), 0.0);
+    for (const auto& notional : notionals) {
+        auto it = std::find(allPayoffs.begin(), allPayoffs.end(), notional.first);
+        if (it == allPayoffs.end()) throw std::runtime_error(std::string(who) + " : payoff not found");
+        vnots[size_t(std::distance(allPayoffs.begin(), it))] = notional.second;
+    }
+    return vnots;
+}
+
 // AAD risk, aggregate portfolio (main.h:176-254)
 inline AADRiskResults AADriskAggregate(const std::string& modelId, const std::string& productId,
                                        const std::map<std::string, double>& notionals, const NumericalParam& num)
@@ -99,14 +113,7 @@ inline AADRiskResults AADriskAggregate(const std::string& modelId, const std::st
     const Model<Number>* model = getModel<Number>(modelId);
     const Product<Number>* product = getProduct<Number>(productId);
     if (!model || !product) throw std::runtime_error("AADriskAggregate() : Could not retrieve model and product");
-    const std::vector<std::string>& allPayoffs = product->payoffLabels();
-    std::vector<double> vnots(allPayoffs.size(), 0.0);
-    for (const auto& notional : notionals) {
-        auto it = std::find(allPayoffs.begin(), allPayoffs.end(), notional.first);
-        if (it == allPayoffs.end()) throw std::runtime_error("AADriskAggregate() : payoff not found");
-        vnots[size_t(std::distance(allPayoffs.begin(), it))] = notional.second;
-    }
-    return cfAADrisk(*model, *product, vnots, num);
+    return cfAADrisk(*model, *product, cfNotionalWeights(*product, notionals, "AADriskAggregate()"), num);
 }
 
 // Values and a matrix of risks, payoffs in columns and parameters in rows (main.h:259-265)
@@ -174,12 +181,17 @@ inline DupireRiskResults dupireAADRisk(const std::string& modelId, const std::st
     if (!model) throw std::runtime_error("dupireAADRisk() : Model not found");
     const Dupire<Number>* dupire = dynamic_cast<const Dupire<Number>*>(model);
     if (!dupire) throw std::runtime_error("dupireAADRisk() : Model not a Dupire");
+    const Product<Number>* product = getProduct<Number>(productId);
+    if (!product) throw std::runtime_error("AADriskAggregate() : Could not retrieve model and product");
+    // AADriskAggregate without its label vectors (1081 strings per call that this entry point drops, main.h:399-408)
+    auto rng = cfMakeRng(num);
+    const AADSums sums = cfSimulAADSums(*product, *model, *rng, size_t(num.numPath),
+                                        cfNotionalWeights(*product, notionals, "AADriskAggregate()"));
     DupireRiskResults results;
-    auto simulResults = AADriskAggregate(modelId, productId, notionals, num);
-    results.value = simulResults.riskPayoffValue;
-    results.delta = simulResults.risks[0];
+    results.value = sums.aggSum / num.numPath;
+    results.delta = sums.risks[0];
     results.vega.resize(dupire->spots().size(), dupire->times().size());
-    std::copy(std::next(simulResults.risks.begin()), simulResults.risks.end(), results.vega.begin());
+    std::copy(std::next(sums.risks.begin()), sums.risks.end(), results.vega.begin());
     return results;
 }
 

@@ -68,6 +68,26 @@ def test_config5_autocall_10_assets_vs_reference(cf, ref, sobol, n):
     check_risks(risks, risks_r)
 
 
+@pytest.mark.parametrize("n_assets", [1, 5, 8, 9, 13, 16])
+def test_every_asset_count_bucket_vs_reference(cf, ref, n_assets):
+    """The kernel is instantiated for up to 4 / 8 / 12 / 16 assets: asset counts at and inside the bucket limits
+    (a full last bucket, a nearly empty one, a single asset), autocall and basket, value + AAD risks."""
+    mid, pid, bid = f"dlm_b{n_assets}", f"auto_b{n_assets}", f"bsk_b{n_assets}"
+    for api in (cf, ref):
+        spots = config5(api, mid, pid, n_assets=n_assets)
+        api.put_baskets(np.full(n_assets, 1.0 / n_assets), 2.0, [0.9 * spots.mean(), 1.1 * spots.mean()], bid)
+    n = 4096
+    assert rel_err(cf.value(mid, pid, n, sobol=False), ref.value(mid, pid, n, sobol=False)) < PRICE_TOL
+    pv, rv, risks = cf.aad_risk_one(mid, pid, n, sobol=False)
+    pv_r, rv_r, risks_r = ref.aad_risk_one(mid, pid, n, sobol=False)
+    assert abs(rv / rv_r - 1) < PRICE_TOL and risks.size == risks_r.size
+    check_risks(risks, risks_r)
+    pv, rv, risks = cf.aad_risk_aggregate(mid, bid, [1.0, -0.5], n)
+    pv_r, rv_r, risks_r = ref.aad_risk_aggregate(mid, bid, [1.0, -0.5], n)
+    assert rel_err(pv, pv_r) < PRICE_TOL and abs(rv / rv_r - 1) < PRICE_TOL
+    check_risks(risks, risks_r)
+
+
 def test_per_path_payoffs_autocall(cf, ref):
     config5(cf); config5(ref)
     got = cf.simul_paths("dlm5", "auto5", 777, sobol=False)

@@ -301,6 +301,8 @@ struct cf_plan {
     {
         if (n == 0) throw CfError("cf_b200: n_paths must be > 0");
         if (rngKind == CF_RNG_SOBOL && first + n > 0xffffffffull) throw CfError("cf_b200: Sobol index exceeds 2^32 - 1");
+        // the reference's skipTo takes an unsigned path index (mrg32k3a.h:192); the jump matrices cover 32 bits of pair index
+        if (rngKind != CF_RNG_SOBOL && first + n > (1ull << 32)) throw CfError("cf_b200: mrg32k3a path index exceeds 2^32 - 1");
         if (tablesInFlight) {
             if (UploadBatch::copied()) CF_CUDA(cudaStreamWaitEvent(s, UploadBatch::copied(), 0));
             tablesInFlight = false;
@@ -811,6 +813,7 @@ void rng_run(const cf_rng* rng, int dim, uint64_t first, uint64_t n, int gaussia
     const bool sobol = rng->kind == CF_RNG_SOBOL;
     if (sobol && dim > cf::sobol_max_dim()) throw CfError("cf_b200: Sobol dimension exceeds 1101");
     if (sobol && first + n > 0xffffffffull) throw CfError("cf_b200: Sobol index exceeds 2^32 - 1");
+    if (!sobol && first + n > (1ull << 32)) throw CfError("cf_b200: mrg32k3a path index exceeds 2^32 - 1 (skipTo takes an unsigned, mrg32k3a.h:192)");
     DevBuf<uint32_t> dDir, dInt;
     DevBuf<uint64_t> dJump;
     DevBuf<double> dOut;

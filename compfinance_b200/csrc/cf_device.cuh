@@ -59,7 +59,7 @@ struct SobolThread {
         const uint32_t H = nidx >> kLowBits;
         const uint32_t l = nidx & (kBlock - 1);
         const uint32_t low = ((l ^ (l >> 1)) & (kBlock - 1)) ^ ((H & 1u) << (kLowBits - 1));
-        sel = int(H - H0);
+        sel = int((H - H0) & 1u);      // 0 or 1 for every real path; padding lanes past index 2^32 - 1 wrap around and stay in range
 #pragma unroll
         for (int k = 0; k < kLowBits; ++k) mask[k] = 0u - ((low >> k) & 1u);
     }

@@ -190,6 +190,30 @@ def _config3_lowlevel(eng, time_map=True):
     return tab, mdl, prd
 
 
+@pytest.mark.parametrize("fast", [True, False])
+@pytest.mark.parametrize("rng,first", [("sobol", (1 << 32) - 1 - 3000), ("mrg", (1 << 32) - 3000)])
+def test_top_of_the_path_index_range_vs_oracle(eng, rng, first, fast):
+    """Maximum sizes: the last 3000 paths the 32-bit path index of the reference can address (Sobol point 2^32 - 1,
+    mrg32k3a pair 2^31 - 1), value + AAD through the C ABI against the numpy restatement, north-star kernels and
+    generic kernel; the padding lanes of the last batch lie past the end of the sequence.  One path more is refused."""
+    from compfinance_b200.capi import CfError
+    tab, mdl, prd = _config3_lowlevel(eng, time_map=fast)
+    n, w = 3000, [1.0, 0.5]
+    r = ("sobol",) if rng == "sobol" else ("mrg", 12345, 12346)
+    o = R.dupire_uoc_run(tab, dict(strike=120.0, barrier=150.0, smooth=0.01), r, first, n, w)
+    g = eng.run_aad(mdl, prd, eng.rng(rng), first, n, w, per_path=True)
+    assert np.max(np.abs(g["payoffs"] - o["payoffs"])) < 1e-9
+    assert abs(g["agg_sum"] / o["agg"].sum() - 1) < PRICE_TOL
+    assert abs(g["table_adj"][0] / o["spot_adj"] - 1) < RISK_TOL
+    if fast:      # adjoints of the local vols (init() folded into the sweep)
+        _, v_o = tab.param_risks(o["spot_adj"], o["ybar"], n)
+        check_vega(g["table_adj"][1:].reshape(30, 36) / n, v_o)
+    else:         # adjoints of the interpolated table
+        check_vega(g["table_adj"][1:].reshape(tab.n_steps, -1) / n, o["ybar"] / n)
+    with pytest.raises(CfError, match="2\\^32"):
+        eng.run_aad(mdl, prd, eng.rng(rng), first + 1, n, w)
+
+
 def test_shards_add_up(eng):
     """Disjoint skip-ahead blocks (the multi-GPU partition) sum to the single run."""
     tab, mdl, prd = _config3_lowlevel(eng)

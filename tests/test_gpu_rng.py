@@ -34,6 +34,16 @@ def test_mrg_numerators_bit_exact(eng, dim, first, n, s1, s2):
     assert (got == R.mrg32k3a_numerators(s1, s2, dim, first, n)).all()
 
 
+def test_mrg_top_of_the_index_range_and_limit(eng):
+    """Path indices up to 2^32 - 1 (the reference's skipTo takes an unsigned): skip-ahead over 2^31 pairs x dim numbers."""
+    from compfinance_b200.capi import CfError
+    first, n = (1 << 32) - 301, 301
+    got = eng.mrg_numerators(eng.rng("mrg", 12345, 12346), 12, first, n)
+    assert (got == R.mrg32k3a_numerators(12345, 12346, 12, first, n)).all()
+    with pytest.raises(CfError, match="2\\^32"):
+        eng.mrg_numerators(eng.rng("mrg", 12345, 12346), 12, (1 << 32) - 5, 10)
+
+
 def test_uniforms_bit_exact_and_golden(eng):
     u = eng.rng_draw(eng.rng("sobol"), 4, 1000, 4, False)
     assert (u == np.array(GOLD["sobol_uniforms_dim4_first1000_n4"])).all()

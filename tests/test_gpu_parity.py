@@ -113,6 +113,42 @@ def test_ragged_path_counts_vs_reference(cf, ref, n, sobol):
     assert np.max(np.abs(vega - rvega)) < 1e-8 * max(np.max(np.abs(rvega)), 1e-3)
 
 
+@pytest.mark.parametrize("weeks", [1, 2, 3, 5, 6, 7, 9, 53, 157, 158, 159])
+def test_step_counts_around_the_chunk_size_vs_reference(cf, ref, weeks):
+    """The north-star kernels work on chunks of 4 steps (Gaussians, history sectors, reverse groups): step counts
+    1, 2, 3 (less than a chunk), 5-7 and 157-159 (every remainder), with an odd path count, against the reference."""
+    for api in (cf, ref):
+        put_config3(api, "dupw", "uocw")
+        api.put_barrier(105.0, 125.0, weeks / 52.0, 1.0 / 52, 0.01, False, f"uoc_w{weeks}")
+    n = 2048 + 17
+    assert cf.describe("dupw", f"uoc_w{weeks}")["n_steps"] == weeks
+    want = ref.value("dupw", f"uoc_w{weeks}", n)
+    assert rel_err(cf.value("dupw", f"uoc_w{weeks}", n), want) < PRICE_TOL
+    val, delta, vega = cf.dupire_aad_risk("dupw", f"uoc_w{weeks}", [1.0, 0.5], 30, 36, n)
+    rval, rdelta, rvega = ref.dupire_aad_risk("dupw", f"uoc_w{weeks}", [1.0, 0.5], 30, 36, n)
+    assert abs(val / rval - 1) < PRICE_TOL and abs(delta / rdelta - 1) < RISK_TOL
+    check_vega(vega, rvega)
+
+
+@pytest.mark.parametrize("m,n_t", [(2, 1), (3, 2), (7, 36), (29, 3), (30, 1), (31, 5), (40, 36)])
+def test_surface_shapes_vs_reference(cf, ref, m, n_t):
+    """Local-vol surfaces from 2 x 1 knots up to more spot knots than the north-star kernels hold (30: beyond that the
+    generic kernel takes over), a single time column (flat in time everywhere), against the reference."""
+    spots = np.linspace(60.0, 180.0, m)
+    times = np.linspace(0.1, 1.4, n_t) if n_t > 1 else np.array([0.5])
+    vols = 0.16 + 0.08 * np.log(spots[:, None] / 100.0) ** 2 + 0.03 * times[None, :]
+    for api in (cf, ref):
+        api.put_dupire(100.0, spots, times, vols, 0.25, f"dup_{m}_{n_t}")
+        api.put_barrier(105.0, 135.0, 1.0, 1.0 / 52, 0.01, False, "uoc_1y")
+    n = 4096 + 33
+    mid = f"dup_{m}_{n_t}"
+    assert rel_err(cf.value(mid, "uoc_1y", n), ref.value(mid, "uoc_1y", n)) < PRICE_TOL
+    val, delta, vega = cf.dupire_aad_risk(mid, "uoc_1y", [1.0, 0.25], m, n_t, n)
+    rval, rdelta, rvega = ref.dupire_aad_risk(mid, "uoc_1y", [1.0, 0.25], m, n_t, n)
+    assert abs(val / rval - 1) < PRICE_TOL and abs(delta / rdelta - 1) < RISK_TOL
+    check_vega(vega, rvega)
+
+
 def test_live_path_regimes_vs_reference(cf, ref):
     """The reverse kernel sweeps only the paths with a non-zero payoff adjoint (the reference's tape skips
     zero-adjoint nodes, AADNode.h:76).  Regimes: many live paths per block (the European payoff carries weight:

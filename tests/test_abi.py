@@ -74,3 +74,24 @@ def test_fails_loudly_without_gpu(built):
     cf.put_european(100, 1.0, 1.0, "eur")
     with pytest.raises(CfHostError, match="no CUDA device"):
         cf.value("bs", "eur", 1024)
+
+
+def test_bench_reference_arm_contract(ref):
+    """`bench.py --impl reference` (the reference's own CPU path on the host cores) prints ONE JSON line with the
+    contract's keys; under torchrun only rank 0 works and prints."""
+    import json
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "paths/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert other.returncode == 0 and other.stdout.strip() == ""

@@ -352,7 +352,9 @@ def main():
         traffic = None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "latest_kernel.json")))
-            traffic = prof.get("dram_bytes_per_launch")
+            traffic = prof.get("dram_bytes_per_launch")       # ncu capture of one 2^20-path launch pair
+            if traffic and world > 1:
+                traffic = traffic * count / N_PATHS            # a rank's shard: history traffic is proportional to its paths
         except OSError:
             pass
         roofline = {

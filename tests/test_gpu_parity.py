@@ -250,6 +250,32 @@ def test_top_of_the_path_index_range_vs_oracle(eng, rng, first, fast):
         eng.run_aad(mdl, prd, eng.rng(rng), first + 1, n, w)
 
 
+@pytest.mark.parametrize("rng,first", [("sobol", 0), ("sobol", 777), ("sobol", (1 << 32) - 1 - 2500),
+                                       ("mrg", 0), ("mrg", 12345), ("mrg", (1 << 32) - 2500)])
+def test_black_scholes_shards_through_the_c_abi_vs_oracle(eng, rng, first):
+    """Black-Scholes x UOC with rates and dividends through the C ABI (first_path / n_paths as a rank of a multi-GPU
+    run passes them): shards from the start, from an odd path (mrg32k3a: the antithetic half of a pair) and at the top
+    of the index range; per-path payoffs, aggregate and every table adjoint against the numpy restatement."""
+    ptl = R.uoc_timeline(1.0, 1.0 / 52)
+    tb = R.BSTables(100, 0.15, 0.03, 0.01, ptl, ptl, [None] * len(ptl), [False] * (len(ptl) - 1) + [True])
+    mdl = eng.bs_model(100.0, tb.drifts, tb.stds, tb.is_event, tb.numeraires, tb.fwd_factors, tb.discounts)
+    smooth = float(100.0 * tb.fwd_factors[0] * 0.01)
+    prd = eng.uoc(100.0, 120.0, smooth, len(ptl))
+    n, w = 2500, [1.0, 0.25]
+    r = ("sobol",) if rng == "sobol" else ("mrg", 12345, 12346)
+    o = R.bs_run(tb, "uoc", dict(strike=100, barrier=120, smooth=0.01), r, first, n, w)
+    g = eng.run_aad(mdl, prd, eng.rng(rng), first, n, w, per_path=True)
+    assert np.max(np.abs(g["payoffs"] - o["payoffs"])) < 1e-10
+    assert abs(g["agg_sum"] / o["agg"].sum() - 1) < PRICE_TOL
+    D, E = tb.n_steps, len(ptl)
+    got, want = g["table_adj"], o["table_adj"]
+    assert got.size == 1 + 2 * D + 4 * E and not np.any(got[1 + 2 * D + 3 * E:])       # no libors in a barrier's samples
+    scale = np.max(np.abs(want))
+    assert np.max(np.abs(got[:want.size] - want)) < RISK_TOL * scale
+    risks = tb.param_risks(got[:want.size], n)
+    assert rel_err(risks, tb.param_risks(want, n)) < RISK_TOL
+
+
 def test_shards_add_up(eng):
     """Disjoint skip-ahead blocks (the multi-GPU partition) sum to the single run."""
     tab, mdl, prd = _config3_lowlevel(eng)

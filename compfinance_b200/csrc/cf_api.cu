@@ -159,13 +159,13 @@ KernelFn pick(int mdl, int prd, bool aad, int rng)
     return fn;
 }
 
-size_t smem_for(int mdl, bool aad, int D, int m, int E, int dim, bool sobol, int lutN, int nPayRows)
+size_t smem_for(int mdl, bool aad, int D, int m, int E, int dim, bool sobol, int lutN, int nPayRows, bool big = false)
 {
     if (mdl == CF_MODEL_DUPIRE)
-        return aad ? cf::smem_sizes<CF_MODEL_DUPIRE, true>(D, m, E, dim, sobol, lutN, nPayRows).total
-                   : cf::smem_sizes<CF_MODEL_DUPIRE, false>(D, m, E, dim, sobol, lutN, nPayRows).total;
-    return aad ? cf::smem_sizes<CF_MODEL_BS, true>(D, m, E, dim, sobol, lutN, nPayRows).total
-               : cf::smem_sizes<CF_MODEL_BS, false>(D, m, E, dim, sobol, lutN, nPayRows).total;
+        return aad ? cf::smem_sizes<CF_MODEL_DUPIRE, true>(D, m, E, dim, sobol, lutN, nPayRows, big).total
+                   : cf::smem_sizes<CF_MODEL_DUPIRE, false>(D, m, E, dim, sobol, lutN, nPayRows, big).total;
+    return aad ? cf::smem_sizes<CF_MODEL_BS, true>(D, m, E, dim, sobol, lutN, nPayRows, big).total
+               : cf::smem_sizes<CF_MODEL_BS, false>(D, m, E, dim, sobol, lutN, nPayRows, big).total;
 }
 
 size_t adj_size(const cf_model* mdl)
@@ -332,8 +332,14 @@ struct cf_plan {
         a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg;
         a.hist = g_scratch.hist.p;
         KernelFn fn = pick(mdlKind, prdKind, aad, rngKind);
-        const size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL, lutN, prdKind == CF_PRODUCT_EUROPEANS ? nPay : 0);
-        if (smem > 227 * 1024) throw CfError("cf_b200: tables do not fit in shared memory (n_steps * n_knots too large)");
+        const int payRows = prdKind == CF_PRODUCT_EUROPEANS ? nPay : 0;
+        size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL, lutN, payRows);
+        if (smem > kFastSmemLimit) {
+            // long schedules: table A and the table adjoints leave shared memory (KArgs::big_tables)
+            a.big_tables = 1;
+            smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL, lutN, payRows, true);
+        }
+        if (smem > kFastSmemLimit) throw CfError("cf_b200: tables do not fit in shared memory (n_steps or n_payoffs too large)");
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         auto ev = takeEvents();
         CF_CUDA(cudaEventRecord(ev.first, s));

@@ -53,6 +53,8 @@ struct KArgs {
     int      lut_n;                // 0 = no table, use binary search
     double   lut_x0, lut_scale;
     int      store_g;              // 1: keep g_i in the history (needed when some interp_vol ~ 0)
+    int      big_tables;           // 1: table A and the block's table adjoints do not fit in shared memory: A is read from
+                                   //    global memory (L1 / L2) and the adjoints accumulate in the block's row of `partial`
     // product
     int      n_payoffs, is_put;
     double   strike, barrier, smooth, coupon;
@@ -322,13 +324,14 @@ __host__ __device__ inline int row_len(int nKnots) { return MDL == CF_MODEL_DUPI
 struct SmemSizes { size_t tabA, tabB, invdx, adj, wrow, red, gq, tagq, dirlow, base, lut, isev, pay, total; };
 
 template <int MDL, bool AAD>
-__host__ __device__ inline SmemSizes smem_sizes(int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN, int nPayRows = 0)
+__host__ __device__ inline SmemSizes smem_sizes(int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN, int nPayRows = 0,
+                                                bool bigTables = false)
 {
     SmemSizes s{};
-    s.tabA = align16(sizeof(double) * table_a_size<MDL>(nSteps, nKnots));
+    s.tabA = bigTables ? 0 : align16(sizeof(double) * table_a_size<MDL>(nSteps, nKnots));
     s.tabB = align16(sizeof(double) * table_b_size<MDL>(nSteps, nKnots));
     s.invdx = align16(sizeof(double) * (nKnots > 0 ? nKnots : 1));
-    s.adj = AAD ? align16(sizeof(double) * adj_table_size<MDL>(nSteps, nKnots, nEvents)) : 0;
+    s.adj = (AAD && !bigTables) ? align16(sizeof(double) * adj_table_size<MDL>(nSteps, nKnots, nEvents)) : 0;
     s.wrow = AAD ? align16(sizeof(double2) * 2 * kWarps * row_len<MDL>(nKnots)) : 0;
     s.red = align16(sizeof(double) * kWarps);
     s.gq = align16(sizeof(double) * kWarps * kChunk * 32);
@@ -346,9 +349,10 @@ __host__ __device__ inline SmemSizes smem_sizes(int nSteps, int nKnots, int nEve
 }
 
 template <int MDL, bool AAD>
-__device__ inline Smem carve(unsigned char* p, int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN, int nPayRows)
+__device__ inline Smem carve(unsigned char* p, int nSteps, int nKnots, int nEvents, int dim, bool sobol, int lutN, int nPayRows,
+                             bool bigTables)
 {
-    const SmemSizes z = smem_sizes<MDL, AAD>(nSteps, nKnots, nEvents, dim, sobol, lutN, nPayRows);
+    const SmemSizes z = smem_sizes<MDL, AAD>(nSteps, nKnots, nEvents, dim, sobol, lutN, nPayRows, bigTables);
     Smem s{};
     s.tabA = reinterpret_cast<double*>(p);    p += z.tabA;
     s.tabB = reinterpret_cast<double*>(p);    p += z.tabB;
@@ -483,13 +487,20 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
     constexpr bool kDupire = (MDL == CF_MODEL_DUPIRE);
     constexpr bool kManyPay = (PRD == CF_PRODUCT_EUROPEANS);
     const int nPayRows = kManyPay ? a.n_payoffs : 0;
-    const Smem sm = carve<MDL, AAD>(smem_raw, D, m, E, a.dim, kSobol, a.lut_n, nPayRows);
+    const bool big = a.big_tables != 0;
+    Smem sm = carve<MDL, AAD>(smem_raw, D, m, E, a.dim, kSobol, a.lut_n, nPayRows, big);
     const int rowLen = row_len<MDL>(m);
     const int nAdj = adj_table_size<MDL>(D, m, E);
     const bool storeG = !kDupire || a.store_g != 0;
+    if (big) {
+        // long schedules (n_steps * n_knots beyond shared memory): table A stays in global memory, the table adjoints
+        // accumulate directly in this block's row of `partial` (one thread per entry: no race, program order)
+        sm.tabA = const_cast<double*>(a.tabA);
+        sm.adj = a.partial + size_t(blockIdx.x) * a.partial_stride + a.n_payoffs + 2;
+    }
 
     // ---- stage tables
-    for (int i = tid; i < table_a_size<MDL>(D, m); i += kBlock) sm.tabA[i] = a.tabA[i];
+    if (!big) for (int i = tid; i < table_a_size<MDL>(D, m); i += kBlock) sm.tabA[i] = a.tabA[i];
     for (int i = tid; i < table_b_size<MDL>(D, m); i += kBlock) sm.tabB[i] = a.tabB[i];
     if (kDupire) {
         for (int i = tid; i + 1 < m; i += kBlock) sm.invdx[i] = 1.0 / (a.tabB[i + 1] - a.tabB[i]);
@@ -735,7 +746,7 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
         s = block_sum(spotBar, sm.red);
         if (tid == 0) out[a.n_payoffs + 1] = s;
         __syncthreads();
-        for (int i = tid; i < nAdj; i += kBlock) out[a.n_payoffs + 2 + i] = sm.adj[i];
+        if (!big) for (int i = tid; i < nAdj; i += kBlock) out[a.n_payoffs + 2 + i] = sm.adj[i];
     }
 }
 

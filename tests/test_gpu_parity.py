@@ -149,6 +149,24 @@ def test_surface_shapes_vs_reference(cf, ref, m, n_t):
     check_vega(vega, rvega)
 
 
+@pytest.mark.parametrize("freq,maturity,steps", [(1.0 / 252, 3.0, 756), (1.0 / 52, 10.0, 520), (1.0 / 252, 1.0, 252)])
+def test_long_schedules_vs_reference(cf, ref, freq, maturity, steps):
+    """Daily monitoring over three years and weekly over ten: n_steps x n_knots tables beyond shared memory (the generic
+    kernel reads table A from global memory and accumulates the table adjoints in its block's row), ten years also run
+    past the last time knot of the surface.  Value and full AAD risk against the reference, both generators."""
+    for api in (cf, ref):
+        put_config3(api, "dupL", "uocL0")
+        api.put_barrier(120.0, 150.0, maturity, freq, 0.01, False, "uocL")
+    assert cf.describe("dupL", "uocL")["n_steps"] == steps
+    n = 2048 + 5
+    for sobol in ((True, False) if steps <= 1101 else (False,)):
+        assert rel_err(cf.value("dupL", "uocL", n, sobol=sobol), ref.value("dupL", "uocL", n, sobol=sobol)) < PRICE_TOL
+        val, delta, vega = cf.dupire_aad_risk("dupL", "uocL", [1.0, 0.5], 30, 36, n, sobol=sobol)
+        rval, rdelta, rvega = ref.dupire_aad_risk("dupL", "uocL", [1.0, 0.5], 30, 36, n, sobol=sobol)
+        assert abs(val / rval - 1) < PRICE_TOL and abs(delta / rdelta - 1) < RISK_TOL
+        check_vega(vega, rvega)
+
+
 def test_live_path_regimes_vs_reference(cf, ref):
     """The reverse kernel sweeps only the paths with a non-zero payoff adjoint (the reference's tape skips
     zero-adjoint nodes, AADNode.h:76).  Regimes: many live paths per block (the European payoff carries weight:

@@ -167,6 +167,44 @@ def test_long_schedules_vs_reference(cf, ref, freq, maturity, steps):
         check_vega(vega, rvega)
 
 
+ODD_CASES = {
+    # name: (spots, times, max_dt, barrier args (strike, barrier, maturity, freq, smooth, put))
+    "one_knot": (np.array([100.0]), np.array([1.0]), 0.25, (105.0, 130.0, 1.0, 1.0 / 52, 0.01, False)),
+    "one_spot_knot_three_times": (np.array([90.0]), np.array([0.2, 0.6, 1.5]), 0.25, (105.0, 130.0, 1.0, 1.0 / 52, 0.01, False)),
+    "fill_steps_between_events": (None, None, 0.01, (105.0, 130.0, 1.0, 1.0 / 52, 0.01, False)),
+    "barrier_below_spot": (None, None, 0.25, (80.0, 95.0, 1.0, 1.0 / 52, 0.01, False)),
+    "barrier_at_spot": (None, None, 0.25, (80.0, 100.0, 1.0, 1.0 / 52, 0.01, False)),
+    "no_smoothing": (None, None, 0.25, (105.0, 130.0, 1.0, 1.0 / 52, 0.0, False)),
+    "wide_smoothing": (None, None, 0.25, (105.0, 130.0, 1.0, 1.0 / 52, 0.25, False)),
+    "strike_above_barrier": (None, None, 0.25, (140.0, 130.0, 1.0, 1.0 / 52, 0.01, False)),
+    "put_monitored_monthly": (None, None, 0.25, (95.0, 125.0, 2.0, 1.0 / 12, 0.02, True)),
+    "single_monitoring_date": (None, None, 0.25, (105.0, 130.0, 0.5, 1.0, 0.01, False)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(ODD_CASES))
+@pytest.mark.parametrize("sobol", [True, False])
+def test_odd_products_and_surfaces_vs_reference(cf, ref, case, sobol):
+    """Degenerate surfaces (a single knot), simulation steps between event dates, barriers at or below the spot
+    (every path dies on the first sample), no smoothing and very wide smoothing, strike above the barrier, a put,
+    one monitoring date: value, per-path payoffs and AAD risks against the reference."""
+    spots, times, max_dt, bar = ODD_CASES[case]
+    if spots is None:
+        spots, times, _ = config3_surface()
+    vols = 0.15 + 0.10 * np.log(spots[:, None] / 100.0) ** 2 + 0.02 * times[None, :]
+    for api in (cf, ref):
+        api.put_dupire(100.0, spots, times, vols, max_dt, "dup_odd")
+        api.put_barrier(*bar, "uoc_odd")
+    n = 2048 + 9
+    got, want = cf.simul_paths("dup_odd", "uoc_odd", n, sobol=sobol), ref.simul_paths("dup_odd", "uoc_odd", n, sobol=sobol)
+    assert np.max(np.abs(got - want)) < 1e-9
+    val, delta, vega = cf.dupire_aad_risk("dup_odd", "uoc_odd", [1.0, 0.5], spots.size, times.size, n, sobol=sobol)
+    rval, rdelta, rvega = ref.dupire_aad_risk("dup_odd", "uoc_odd", [1.0, 0.5], spots.size, times.size, n, sobol=sobol)
+    assert abs(val - rval) < PRICE_TOL * max(1.0, abs(rval))
+    assert abs(delta - rdelta) < RISK_TOL * max(abs(rdelta), 1e-3)
+    check_vega(vega, rvega)
+
+
 def test_live_path_regimes_vs_reference(cf, ref):
     """The reverse kernel sweeps only the paths with a non-zero payoff adjoint (the reference's tape skips
     zero-adjoint nodes, AADNode.h:76).  Regimes: many live paths per block (the European payoff carries weight:

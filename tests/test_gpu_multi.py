@@ -88,6 +88,50 @@ def test_every_asset_count_bucket_vs_reference(cf, ref, n_assets):
     check_risks(risks, risks_r)
 
 
+def _dlm_case(api, name):
+    """Odd corners of the displaced model and the autocallable; returns (model id, product id)."""
+    a = np.arange(4)
+    spots, atms = 100.0 + 10 * a, 0.2 + 0.03 * a
+    skews = np.array([0.0, -0.2, 0.15, -0.05])            # all four dynamics
+    correl = np.full((4, 4), 0.3) + 0.7 * np.eye(4)
+    kw = dict(spots=spots, atms=atms, skews=skews, rate=0.03, repo=0.002 * a, div_dates=[0.4, 1.1],
+              divs=np.full((2, 4), 0.015), correl=correl, lam=0.2)
+    auto = dict(refs=spots, maturity=2.0, periods=8, ko=1.0, strike=0.8, cpn=0.08, smooth=0.02)
+    if name == "no_dividends": kw.update(div_dates=[], divs=np.zeros((0, 4)))
+    elif name == "dividend_on_an_event_date": kw.update(div_dates=[0.25, 1.0])
+    elif name == "independent_assets": kw.update(correl=np.eye(4), lam=0.0)
+    elif name == "lambda_pushes_to_full_correlation": kw.update(lam=0.95)
+    elif name == "zero_rates": kw.update(rate=0.0, repo=np.zeros(4))
+    elif name == "one_period": auto.update(periods=1)
+    elif name == "knock_out_far_away": auto.update(ko=3.0)
+    elif name == "knocked_out_on_the_first_date": auto.update(ko=0.2)
+    elif name == "thin_smoothing": auto.update(smooth=1e-6)
+    elif name == "strike_above_par": auto.update(strike=1.3)
+    elif name == "references_off_the_spots": auto.update(refs=spots * np.array([0.8, 1.0, 1.2, 1.05]))
+    api.put_displaced(kw["spots"], kw["atms"], kw["skews"], kw["rate"], kw["repo"], kw["div_dates"], kw["divs"], kw["correl"],
+                      kw["lam"], "dlm_odd")
+    api.put_autocall(auto["refs"], auto["maturity"], auto["periods"], auto["ko"], auto["strike"], auto["cpn"], auto["smooth"], "auto_odd")
+    return "dlm_odd", "auto_odd"
+
+
+DLM_CASES = ["no_dividends", "dividend_on_an_event_date", "independent_assets", "lambda_pushes_to_full_correlation", "zero_rates",
+             "one_period", "knock_out_far_away", "knocked_out_on_the_first_date", "thin_smoothing", "strike_above_par",
+             "references_off_the_spots"]
+
+
+@pytest.mark.parametrize("case", DLM_CASES)
+def test_odd_displaced_models_and_autocalls_vs_reference(cf, ref, case):
+    for api in (cf, ref):
+        mid, pid = _dlm_case(api, case)
+    n = 4096 + 3
+    got, want = cf.simul_paths(mid, pid, n, sobol=False), ref.simul_paths(mid, pid, n, sobol=False)
+    assert np.max(np.abs(got - want)) < 1e-11
+    pv, rv, risks = cf.aad_risk_one(mid, pid, n)
+    pv_r, rv_r, risks_r = ref.aad_risk_one(mid, pid, n)
+    assert abs(rv / rv_r - 1) < PRICE_TOL and risks.size == risks_r.size
+    check_risks(risks, risks_r)
+
+
 def test_per_path_payoffs_autocall(cf, ref):
     config5(cf); config5(ref)
     got = cf.simul_paths("dlm5", "auto5", 777, sobol=False)

@@ -62,6 +62,39 @@ def test_config2_full_size(cf):
     assert np.max(np.abs(risks[2:] - np.array(g["risks"][2:]))) < 1e-8 * max(1.0, np.max(np.abs(g["risks"])))
 
 
+BS_CASES = {
+    # name: ((spot, vol, rate, div), product kind, product args)
+    "late_settlement": ((100.0, 0.2, 0.03, 0.01), "european", (105.0, 1.0, 1.5)),
+    "negative_rates": ((100.0, 0.2, -0.01, 0.0), "european", (95.0, 2.0, 2.0)),
+    "dividends_above_rates": ((100.0, 0.25, 0.01, 0.06), "barrier", (100.0, 125.0, 1.5, 1.0 / 52, 0.01, False)),
+    "high_vol_daily_barrier": ((100.0, 0.6, 0.02, 0.0), "barrier", (100.0, 160.0, 1.0, 1.0 / 252, 0.01, False)),
+    "tiny_vol": ((100.0, 1e-4, 0.05, 0.0), "barrier", (100.0, 104.0, 1.0, 1.0 / 12, 0.01, False)),
+    "put_barrier": ((100.0, 0.2, 0.03, 0.02), "barrier", (110.0, 130.0, 1.0, 1.0 / 52, 0.02, True)),
+    "short_expiry": ((100.0, 0.2, 0.03, 0.0), "european", (100.0, 1.0 / 365, 1.0 / 365)),
+    "ladder": ((100.0, 0.2, 0.03, 0.01), "europeans", ([0.5, 0.5, 1.0, 1.0, 2.0], [90.0, 110.0, 100.0, 100.0, 120.0])),
+}
+
+
+@pytest.mark.parametrize("case", sorted(BS_CASES))
+@pytest.mark.parametrize("sobol", [True, False])
+def test_odd_black_scholes_cases_vs_reference(cf, ref, case, sobol):
+    """Black-Scholes corners: settlement after exercise (forward and discount factors), negative rates, dividends above
+    rates, daily monitoring at high vol, almost no vol, a put barrier, a one-day option, a strike ladder with repeated
+    dates and strikes: per-path payoffs and the four AAD risks against the reference."""
+    (spot, vol, rate, div), kind, args = BS_CASES[case]
+    for api in (cf, ref):
+        (api.put_black_scholes if hasattr(api, "put_black_scholes") else api.put_bs)(spot, vol, False, rate, div, "bs_odd")
+        getattr(api, "put_" + kind)(*args, "prd_odd")
+    n = 2048 + 11
+    got, want = cf.simul_paths("bs_odd", "prd_odd", n, sobol=sobol), ref.simul_paths("bs_odd", "prd_odd", n, sobol=sobol)
+    assert np.max(np.abs(got - want)) < 1e-9
+    last = got.shape[1] - 1
+    pv, rv, risks = cf.aad_risk_one("bs_odd", "prd_odd", n, risk_payoff=last, sobol=sobol)
+    pv_r, rv_r, risks_r = ref.aad_risk_one("bs_odd", "prd_odd", n, risk_payoff=last, sobol=sobol)
+    assert abs(rv - rv_r) < PRICE_TOL * max(1.0, abs(rv_r))
+    assert np.max(np.abs(risks - risks_r)) < RISK_TOL * max(1.0, np.max(np.abs(risks_r)))
+
+
 # ---- config 3: Dupire barrier, risk to the whole local-vol surface ---------------------------------
 @pytest.mark.parametrize("name,sobol", [("config3_sobol_16k", True), ("config3_mrg_16k", False)])
 def test_config3_dupire_barrier_golden(cf, name, sobol):

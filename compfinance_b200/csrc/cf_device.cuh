@@ -182,6 +182,13 @@ struct MrgThread {
 
 __device__ __forceinline__ double mrg_uniform(uint32_t z) { return double(z) / 4294967088.0; }
 
+// a / b for b > 0 where a is often exactly zero (adjoints of inactive branches, dead notionals, options out of the
+// money).  CUDA's double division leaves its inline path for a zero numerator and runs the out-of-line routine
+// (~200 instructions); 0 / b is a itself, signed zero included, so the result is bit for bit the quotient.
+__device__ __forceinline__ double div_z(double a, double b) { return a == 0.0 ? a : a / b; }
+// the same for a numeraire-like divisor that is often exactly 1 (models without rates leave the Sample default): a / 1 = a
+__device__ __forceinline__ double div_n(double a, double num) { return (a == 0.0 || num == 1.0) ? a : a / num; }
+
 // ---------------------------------------------------------------------------------------------
 // Deterministic reductions
 // ---------------------------------------------------------------------------------------------

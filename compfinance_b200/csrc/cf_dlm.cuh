@@ -195,21 +195,21 @@ __global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(
 #pragma unroll
                 for (int k = 1; k < AMAX; ++k)
                     if (k < A) { const double pf = F[k] / __ldg(a.pweights + k); if (pf < worst) worst = pf; }
-                pay += alive * a.coupon * a.cpn_dt / num;
+                pay += div_z(alive * a.coupon * a.cpn_dt, num);
                 if (e < E - 1) {
                     const double f = fmin(1.0, fmax(0.0, (a.ko + a.smooth - worst) / 2 / a.smooth));
                     const double surv = alive * f;
-                    pay += (alive - surv) / num;
+                    pay += div_z(alive - surv, num);
                     alive = surv;
                 } else {
-                    pay += alive / num;
-                    pay -= alive * fmax(a.strike - worst, 0.0) / a.strike / num;
+                    pay += div_z(alive, num);
+                    pay -= div_z(div_z(alive * fmax(a.strike - worst, 0.0), a.strike), num);
                 }
             } else if (PRD == CF_PRODUCT_BASKETS) {
                 double b = 0.0;
 #pragma unroll
                 for (int k = 0; k < AMAX; ++k) if (k < A) b += __ldg(a.pweights + k) * F[k];
-                for (int k = 0; k < a.n_strikes; ++k) emit(k, fmax(b - __ldg(a.strikes + k), 0.0) / num);
+                for (int k = 0; k < a.n_strikes; ++k) emit(k, div_z(fmax(b - __ldg(a.strikes + k), 0.0), num));
             } else {                                       // MultiStats: levels now, differences after all levels
                 for (int a1 = 0; a1 < A; ++a1) emit(payIdx++, F[a1]);
                 for (int a1 = 0; a1 < A; ++a1)
@@ -296,18 +296,18 @@ __global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(
                         const double q = (a.ko + a.smooth - worst) / 2 / a.smooth;
                         const double f = fmin(1.0, fmax(0.0, q));
                         // surv = alive f; pay += alive cpn dt / num + alive (1 - f) / num
-                        const double fbar = alivebar * aliveBefore - paybar * aliveBefore / num;
+                        const double fbar = alivebar * aliveBefore - div_z(paybar * aliveBefore, num);
                         const double qbar = (q > 0.0 && q < 1.0) ? fbar : 0.0;      // max(0, .) then min(1, .), strict (AADExpr.h:571-598)
-                        worstbar = -qbar / sm2;
-                        numbar = -paybar * (aliveBefore * a.coupon * a.cpn_dt + (aliveBefore - aliveBefore * f)) / (num * num);
-                        alivebar = alivebar * f + paybar * a.coupon * a.cpn_dt / num + paybar * (1.0 - f) / num;
+                        worstbar = div_z(-qbar, sm2);
+                        numbar = div_z(-paybar * (aliveBefore * a.coupon * a.cpn_dt + (aliveBefore - aliveBefore * f)), num * num);
+                        alivebar = alivebar * f + paybar * a.coupon * a.cpn_dt / num + div_z(paybar * (1.0 - f), num);
                     } else {
                         const double put = fmax(a.strike - worst, 0.0);
-                        worstbar = (a.strike - worst > 0.0) ? paybar * aliveBefore / a.strike / num : 0.0;
-                        numbar = -paybar * (aliveBefore * a.coupon * a.cpn_dt + aliveBefore - aliveBefore * put / a.strike) / (num * num);
-                        alivebar = paybar * (a.coupon * a.cpn_dt / num + 1.0 / num - put / a.strike / num);
+                        worstbar = (a.strike - worst > 0.0) ? div_z(div_z(paybar * aliveBefore, a.strike), num) : 0.0;
+                        numbar = div_z(-paybar * (aliveBefore * a.coupon * a.cpn_dt + aliveBefore - div_z(aliveBefore * put, a.strike)), num * num);
+                        alivebar = paybar * (a.coupon * a.cpn_dt / num + 1.0 / num - div_z(div_z(put, a.strike), num));
                     }
-                    const double fb = worstbar / __ldg(a.pweights + am);      // one division: only the worst performer carries the adjoint
+                    const double fb = div_z(worstbar, __ldg(a.pweights + am));      // one division: only the worst performer carries the adjoint
 #pragma unroll
                     for (int k = 0; k < AMAX; ++k) if (k == am) Fbar[k] = fb;
                 } else if (PRD == CF_PRODUCT_BASKETS) {
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(
                     double bbar = 0.0;
                     for (int k = 0; k < a.n_strikes; ++k) {
                         const double x = b - __ldg(a.strikes + k);
-                        if (x > 0.0) { bbar += a.w[k] / num; numbar -= a.w[k] * x / (num * num); }
+                        if (x > 0.0) { bbar += div_z(a.w[k], num); numbar -= div_z(a.w[k] * x, num * num); }
                     }
 #pragma unroll
                     for (int k = 0; k < AMAX; ++k) if (k < A) Fbar[k] = bbar * __ldg(a.pweights + k);

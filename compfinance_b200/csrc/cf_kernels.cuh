@@ -221,7 +221,7 @@ template <> struct Product<CF_PRODUCT_EUROPEANS> {
     {
         const double F = s.fwd(), num = s.num();
         const int k1 = __ldg(off + e + 1);
-        for (int k = __ldg(off + e); k < k1; ++k) c.emit(k, fmax(F - __ldg(K + k), 0.0) / num);
+        for (int k = __ldg(off + e); k < k1; ++k) c.emit(k, div_n(fmax(F - __ldg(K + k), 0.0), num));
     }
     __device__ void payoffs(double*) const {}
     __device__ void begin_reverse(const double*) {}
@@ -234,8 +234,8 @@ template <> struct Product<CF_PRODUCT_EUROPEANS> {
             const double x = F - __ldg(K + k);
             if (x > 0.0) {                               // max(x, 0): derivative 1 iff x > 0 (AADExpr.h:571-583)
                 const double wk = __ldg(w + k);
-                r.fwd += wk / num;
-                r.num -= wk * x / (num * num);
+                r.fwd += div_n(wk, num);
+                r.num -= div_n(wk * x, num * num);
             }
         }
         return r;

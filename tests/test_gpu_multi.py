@@ -106,6 +106,7 @@ def _dlm_case(api, name):
     elif name == "knock_out_far_away": auto.update(ko=3.0)
     elif name == "knocked_out_on_the_first_date": auto.update(ko=0.2)
     elif name == "thin_smoothing": auto.update(smooth=1e-6)
+    elif name == "no_smoothing": auto.update(smooth=0.0)      # digital knock-out: the adjoint of the smoothing ratio is 0 / 0 unless skipped
     elif name == "strike_above_par": auto.update(strike=1.3)
     elif name == "references_off_the_spots": auto.update(refs=spots * np.array([0.8, 1.0, 1.2, 1.05]))
     api.put_displaced(kw["spots"], kw["atms"], kw["skews"], kw["rate"], kw["repo"], kw["div_dates"], kw["divs"], kw["correl"],
@@ -115,7 +116,7 @@ def _dlm_case(api, name):
 
 
 DLM_CASES = ["no_dividends", "dividend_on_an_event_date", "independent_assets", "lambda_pushes_to_full_correlation", "zero_rates",
-             "one_period", "knock_out_far_away", "knocked_out_on_the_first_date", "thin_smoothing", "strike_above_par",
+             "one_period", "knock_out_far_away", "knocked_out_on_the_first_date", "thin_smoothing", "no_smoothing", "strike_above_par",
              "references_off_the_spots"]
 
 

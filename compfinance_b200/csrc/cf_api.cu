@@ -93,12 +93,13 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     // stream-ordered allocations from the device's default pool (kept by the pool after the first call)
     ~DevBuf() { release(); }
-    void release() { if (p && owned) cudaFreeAsync(p, nullptr); p = nullptr; owned = true; }
-    void alloc(size_t count)
+    // allocation and release are ordered on stream s (the stream the buffer is used on; nullptr: the legacy default stream)
+    void release(cudaStream_t s = nullptr) { if (p && owned) cudaFreeAsync(p, s); p = nullptr; n = 0; owned = true; }
+    void alloc(size_t count, cudaStream_t s = nullptr)
     {
-        release();
+        release(s);
         n = count;
-        if (count) CF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), nullptr));
+        if (count) CF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), s));
     }
     void upload(const T* src, size_t count, cudaStream_t s = nullptr)
     {
@@ -141,14 +142,14 @@ struct UploadScope {
     ~UploadScope() { if (UploadBatch::current() == &batch) UploadBatch::current() = nullptr; }
 };
 
-// Scratch shared by all plans of the process (one run at a time per context): path history,
-// per-block partials, per-warp vol-adjoint tables.  Grown on demand, never shrunk.
+// Scratch of one plan: path history, per-block partials, per-warp vol-adjoint tables.  Grown on demand on the launch
+// stream (stream-ordered allocation: a buffer is only released after the work queued before it on that stream), never
+// shrunk.  A plan is used on one stream at a time; two plans never share scratch.
 struct Scratch {
     DevBuf<double> hist, state, partial, partialRev, wtab, btab, tmp;
     DevBuf<uint32_t> live;
-    void need(DevBuf<double>& b, size_t n) { if (b.n < n) b.alloc(n); }
+    template <class T> void need(DevBuf<T>& b, size_t n, cudaStream_t s) { if (b.n < n) b.alloc(n, s); }
 };
-Scratch g_scratch;
 
 using cf::KernelFn;
 
@@ -250,6 +251,7 @@ struct cf_plan {
     uint32_t peerEpoch = 0;
     DevBuf<uint32_t> peerTicket;
     bool tablesInFlight = true;       // the first launch orders its stream after the table upload (null stream)
+    Scratch scratch;
     cf::KArgs base{};
     DevBuf<uint8_t> isEvent;
     DevBuf<double> tabA, tabB, num, ff, disc, libors, eventDt;
@@ -317,8 +319,8 @@ struct cf_plan {
         const size_t tabAdj = mdlKind == CF_MODEL_DUPIRE ? 1 + size_t(D) * m : nAdj;   // generic kernel: table adjoints
         const size_t stride = aad ? size_t(nPay) + 1 + tabAdj : size_t(nPay);
         partialStride = int(stride);
-        g_scratch.need(g_scratch.partial, size_t(grid) * stride);
-        if (aad) g_scratch.need(g_scratch.hist, size_t(2) * D * size_t(grid) * cf::kBlock);
+        scratch.need(scratch.partial, size_t(grid) * stride, s);
+        if (aad) scratch.need(scratch.hist, size_t(2) * D * size_t(grid) * cf::kBlock, s);
         cf::KArgs a = base;
         a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
         a.w[0] = a.w[1] = 0.0;
@@ -328,9 +330,9 @@ struct cf_plan {
             CF_CUDA(cudaStreamSynchronize(s));
         }
         a.wlong = lW.p;
-        a.partial = g_scratch.partial.p; a.partial_stride = partialStride;
+        a.partial = scratch.partial.p; a.partial_stride = partialStride;
         a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg;
-        a.hist = g_scratch.hist.p;
+        a.hist = scratch.hist.p;
         KernelFn fn = pick(mdlKind, prdKind, aad, rngKind);
         const int payRows = prdKind == CF_PRODUCT_EUROPEANS ? nPay : 0;
         size_t smem = smem_for(mdlKind, aad, D, m, E, dim, rngKind == CF_RNG_SOBOL, lutN, payRows);
@@ -349,14 +351,14 @@ struct cf_plan {
         CF_CUDA(cudaGetLastError());
         if (aad && mdlKind == CF_MODEL_DUPIRE && hasTimeMap) {
             // generic kernel produced interp_vols adjoints: reduce, then apply the time map
-            g_scratch.need(g_scratch.tmp, stride);
-            cf::reduce_partials_kernel<<<(int(stride) + 127) / 128, 128, 0, s>>>(g_scratch.partial.p, grid, partialStride, int(stride), g_scratch.tmp.p);
+            scratch.need(scratch.tmp, stride, s);
+            cf::reduce_partials_kernel<<<(int(stride) + 127) / 128, 128, 0, s>>>(scratch.partial.p, grid, partialStride, int(stride), scratch.tmp.p);
             const int nOut = int(outSize(true));
-            cf::collapse_time_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(g_scratch.tmp.p, nPay + 2, D, m, nTimes, tk1.p, tk2.p, tc1.p, tc2.p, dOut);
+            cf::collapse_time_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(scratch.tmp.p, nPay + 2, D, m, nTimes, tk1.p, tk2.p, tc1.p, tc2.p, dOut);
             g_launches += 1;
         } else {
             const int nOut = int(outSize(aad));
-            cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(g_scratch.partial.p, grid, partialStride, nOut, dOut);
+            cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(scratch.partial.p, grid, partialStride, nOut, dOut);
         }
         CF_CUDA(cudaGetLastError());
         g_launches += 2;
@@ -370,8 +372,8 @@ struct cf_plan {
         const int grid = std::min(nBatches, 2 * g_sms);
         const size_t stride = aad ? size_t(nPay) + 1 + nAdj : size_t(nPay);
         partialStride = int(stride);
-        g_scratch.need(g_scratch.partial, size_t(grid) * stride);
-        if (aad) g_scratch.need(g_scratch.hist, size_t(D) * (2 * A + 1) * size_t(grid) * cf::kBlock);
+        scratch.need(scratch.partial, size_t(grid) * stride, s);
+        if (aad) scratch.need(scratch.hist, size_t(D) * (2 * A + 1) * size_t(grid) * cf::kBlock, s);
         cf::LArgs a = lbase;
         a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
         if (aad) {
@@ -380,8 +382,8 @@ struct cf_plan {
             CF_CUDA(cudaStreamSynchronize(s));
         }
         a.w = lW.p;
-        a.partial = g_scratch.partial.p; a.partial_stride = partialStride;
-        a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg; a.hist = g_scratch.hist.p;
+        a.partial = scratch.partial.p; a.partial_stride = partialStride;
+        a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg; a.hist = scratch.hist.p;
         LKernel fn = cf::pick_dlm_kernel(A, prdKind, aad, rngKind);
         if (!fn) throw CfError("cf_b200: MultiStats is a value-only test instrument on the device (no AAD)");
         const size_t smem = cf::dlm_smem(A, D, E, nPay, dim, rngKind == CF_RNG_SOBOL, aad).total;
@@ -394,7 +396,7 @@ struct cf_plan {
         events.push_back(ev);
         CF_CUDA(cudaGetLastError());
         const int nOut = int(outSize(aad));
-        cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(g_scratch.partial.p, grid, partialStride, nOut, dOut);
+        cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(scratch.partial.p, grid, partialStride, nOut, dOut);
         CF_CUDA(cudaGetLastError());
         g_launches += 2;
     }
@@ -414,9 +416,36 @@ struct cf_plan {
     // n_steps * 8 bytes per path (1.3 GB for 2^20 paths x 156 steps).
     static constexpr uint64_t kFastChunk = 1ull << 21;
 
+    // The reverse sweep has two forms (cf_dupire.cuh): one path per lane, 8 warps (many live paths per SM), and four
+    // lanes per path, 16 warps (few: a shard of a multi-GPU run).  CF_DUPIRE_REV = quad | classic forces one.
+    bool reverseQuad(uint64_t nPad) const
+    {
+        static const int forced = [] {
+            const char* e = std::getenv("CF_DUPIRE_REV");
+            return !e ? 0 : (std::strcmp(e, "quad") == 0 ? 1 : (std::strcmp(e, "classic") == 0 ? 2 : 0));
+        }();
+        if (forced) return forced == 1;
+        return nPad <= uint64_t(g_sms) * 2048;
+    }
+
+    // kernel launch on stream s, optionally with programmatic stream serialization (the kernel may start while its
+    // predecessor runs and waits for it in griddepcontrol.wait)
+    template <class Args>
+    static void launchKernel(void (*fn)(const Args), int grid, int block, size_t smem, cudaStream_t s, const Args& a, bool pdl)
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(unsigned(block)); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+        CF_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    }
+
     void launchFast(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut,
                     double* dPerPath, double* dPerAgg, cudaStream_t s)
     {
+        static const bool pdl = [] { const char* e = std::getenv("CF_PDL"); return !e || std::atoi(e) != 0; }();
         const bool sob = rngKind == CF_RNG_SOBOL;
         const int fwdP = forwardP(std::min<uint64_t>(n, kFastChunk)), fwdWarps = cf::kFwdWarps;
         const uint64_t quantum = 256ull * fwdP;
@@ -425,25 +454,31 @@ struct cf_plan {
         const uint64_t maxPad = (maxChunk + quantum - 1) / quantum * quantum;
         const int maxUnitsF = int(maxPad / quantum) * 8;
         const int gridF = std::min(maxUnitsF, g_sms);       // units are dealt round-robin: small runs still use every SM
-        // reverse blocks own contiguous ranges of live-mask words (32 paths each), at most kRevMaxWords per block
-        const int minGridR = int((maxPad / 32 + cf::kRevMaxWords - 1) / cf::kRevMaxWords);
+        const bool quad = aad && reverseQuad(maxPad);
+        const int revWarps = quad ? cf::kRevQWarps : cf::kRevWarps, revMaxWords = quad ? cf::kRevQMaxWords : cf::kRevMaxWords;
+        // reverse blocks own contiguous ranges of live-mask words (32 paths each), at most revMaxWords per block
+        const int minGridR = int((maxPad / 32 + revMaxWords - 1) / revMaxWords);
         const int gridR = std::max(int(std::min<uint64_t>(maxPad / 32, uint64_t(g_sms))), minGridR);
         const size_t tabLen = size_t(nTimes) * m;
-        g_scratch.need(g_scratch.partial, size_t(gridF) * (size_t(nPay) + 1));
+        scratch.need(scratch.partial, size_t(gridF) * (size_t(nPay) + 1), s);
         if (aad) {
-            g_scratch.need(g_scratch.hist, size_t(histRow) * maxPad);
-            g_scratch.need(g_scratch.state, 2 * maxPad);
-            if (g_scratch.live.n < size_t(maxPad / 32)) g_scratch.live.alloc(size_t(maxPad / 32));
-            g_scratch.need(g_scratch.partialRev, size_t(gridR));
-            g_scratch.need(g_scratch.wtab, size_t(gridR) * cf::kRevWarps * tabLen);
-            g_scratch.need(g_scratch.btab, size_t(gridR) * tabLen);
+            scratch.need(scratch.hist, size_t(histRow) * maxPad, s);
+            scratch.need(scratch.state, 2 * maxPad, s);
+            scratch.need(scratch.live, size_t(maxPad / 32), s);
+            scratch.need(scratch.partialRev, size_t(gridR), s);
+            scratch.need(scratch.wtab, size_t(gridR) * revWarps * tabLen, s);
+            scratch.need(scratch.btab, size_t(gridR) * tabLen, s);
         }
         DKernel fwd;
         size_t smemF;
-        fwd = cf::pick_dupire_forward(prdKind, aad, rngKind, fwdP);
-        smemF = fwdP == 2 ? cf::dupire_smem_fwd4<2>(D, m, dim, sob, nCells, fwdWarps).total : cf::dupire_smem_fwd4<1>(D, m, dim, sob, nCells, fwdWarps).total;
-        auto rev = cf::pick_dupire_reverse(prdKind);
-        const size_t smemR = cf::dupire_smem_rev(D, m, nCells).total;
+        static const int forcedCh = [] { const char* e = std::getenv("CF_DUPIRE_FWD_CH"); return e ? std::atoi(e) : 0; }();
+        const int fwdCh = fwdP == 2 ? cf::kFwdChunk : (forcedCh == cf::kFwdChunk ? cf::kFwdChunk : cf::kFwdChunk1);
+        fwd = cf::pick_dupire_forward(prdKind, aad, rngKind, fwdP, fwdCh);
+        smemF = fwdP == 2 ? cf::dupire_smem_fwd4<2, cf::kFwdChunk>(D, m, dim, sob, nCells, fwdWarps).total
+              : fwdCh == cf::kFwdChunk ? cf::dupire_smem_fwd4<1, cf::kFwdChunk>(D, m, dim, sob, nCells, fwdWarps).total
+                                       : cf::dupire_smem_fwd4<1, cf::kFwdChunk1>(D, m, dim, sob, nCells, fwdWarps).total;
+        auto rev = quad ? cf::pick_dupire_reverse_quad(prdKind) : cf::pick_dupire_reverse(prdKind);
+        const size_t smemR = quad ? cf::dupire_smem_revq(D, m, nCells).total : cf::dupire_smem_rev(D, m, nCells).total;
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fwd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
         if (aad) CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rev), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemR)));
         auto ev = takeEvents();
@@ -456,17 +491,15 @@ struct cf_plan {
             a.accumulate = off ? 1 : 0;
             a.w[0] = a.w[1] = 0.0;
             if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
-            a.partial = g_scratch.partial.p; a.partial_rev = g_scratch.partialRev.p;
-            a.wtab = g_scratch.wtab.p; a.btab = g_scratch.btab.p; a.hist = g_scratch.hist.p; a.state = g_scratch.state.p; a.live = g_scratch.live.p;
+            a.partial = scratch.partial.p; a.partial_rev = scratch.partialRev.p;
+            a.wtab = scratch.wtab.p; a.btab = scratch.btab.p; a.hist = scratch.hist.p; a.state = scratch.state.p; a.live = scratch.live.p;
             a.per_path_payoffs = dPerPath ? dPerPath + off * nPay : nullptr;
             a.per_path_agg = dPerAgg ? dPerAgg + off : nullptr;
             a.n_units = int(a.n_pad / quantum) * 8;
-            fwd<<<gridF, fwdWarps * 32, smemF, s>>>(a);
-            CF_CUDA(cudaGetLastError());
+            launchKernel(fwd, gridF, fwdWarps * 32, smemF, s, a, false);
             ++g_launches;
             if (aad) {
-                rev<<<gridR, cf::kRevBlock, smemR, s>>>(a);
-                CF_CUDA(cudaGetLastError());
+                launchKernel(rev, gridR, revWarps * 32, smemR, s, a, pdl && quad);
                 ++g_launches;
             }
         }
@@ -480,8 +513,8 @@ struct cf_plan {
             if (!peerTicket.p) { peerTicket.alloc(1); CF_CUDA(cudaMemsetAsync(peerTicket.p, 0, sizeof(uint32_t), s)); }
             pr.ticket = peerTicket.p;
         }
-        cf::dupire_reduce_kernel<<<(nOut * 32 + 255) / 256, 256, 0, s>>>(g_scratch.partial.p, gridF, nPay, g_scratch.partialRev.p,
-                                                                        g_scratch.btab.p, gridR, m, nTimes, aad ? 1 : 0, dOut, pr);
+        cf::dupire_reduce_kernel<<<(nOut * 32 + 255) / 256, 256, 0, s>>>(scratch.partial.p, gridF, nPay, scratch.partialRev.p,
+                                                                        scratch.btab.p, gridR, m, nTimes, aad ? 1 : 0, dOut, pr);
         CF_CUDA(cudaGetLastError());
         ++g_launches;
     }
@@ -685,8 +718,10 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 p->k12.upload(colxy.data(), colxy.size());
                 p->flushOps.upload(ops.data(), ops.size());
                     const bool sob = rng->kind == CF_RNG_SOBOL;
-                if (cf::dupire_smem_fwd4<2>(D, m, p->dim, sob, nCells, cf::kFwdWarps).total > kFastSmemLimit
-                    || cf::dupire_smem_rev(D, m, nCells).total > kFastSmemLimit) p->fast = false;
+                if (cf::dupire_smem_fwd4<2, cf::kFwdChunk>(D, m, p->dim, sob, nCells, cf::kFwdWarps).total > kFastSmemLimit
+                    || cf::dupire_smem_fwd4<1, cf::kFwdChunk1>(D, m, p->dim, sob, nCells, cf::kFwdWarps).total > kFastSmemLimit
+                    || cf::dupire_smem_rev(D, m, nCells).total > kFastSmemLimit
+                    || cf::dupire_smem_revq(D, m, nCells).total > kFastSmemLimit) p->fast = false;
                 // Moro's branch test |u - 1/2| < 0.42 (gaussians.h:54) as a range of the RNG integer z: u(z) is
                 // monotone, so the central set is an interval [lo, hi]; searched with the device's own arithmetic
                 // (u = c z for Sobol, z / (m1 + 1) for mrg32k3a; u - 1/2 is exact on both sides of 1/2)
@@ -887,8 +922,6 @@ int cf_shutdown(void)
     return guarded([&] {
         if (g_device >= 0) {
             CF_CUDA(cudaDeviceSynchronize());
-            g_scratch.hist.alloc(0); g_scratch.partial.alloc(0); g_scratch.wtab.alloc(0); g_scratch.btab.alloc(0); g_scratch.tmp.alloc(0);
-            g_scratch.state.alloc(0); g_scratch.partialRev.alloc(0); g_scratch.live.alloc(0);
         }
         g_device = -1;
     });

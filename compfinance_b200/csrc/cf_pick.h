@@ -16,8 +16,10 @@ KernelFn pick_path_kernel(int mdl, int prd, bool aad, int rng);
 MKernel pick_multi_kernel(int rng);
 // cf_pick_dlm.cu: displaced multi-asset model, instantiated for up to 4 / 8 / 12 / 16 assets; nullptr: MultiStats with AAD
 LKernel pick_dlm_kernel(int n_assets, int prd, bool aad, int rng);
-// cf_pick_dupire.cu: the north-star kernels; fwdP = paths per thread of the forward kernel, 1 or 2 (kFwdWarps warps per block)
-DKernel pick_dupire_forward(int prd, bool aad, int rng, int fwdP);
+// cf_pick_dupire.cu: the north-star kernels; fwdP = paths per thread of the forward kernel, 1 or 2 (kFwdWarps warps per block),
+// chunk = steps of Gaussians per fill (kFwdChunk; kFwdChunk1 is also built for fwdP = 1)
+DKernel pick_dupire_forward(int prd, bool aad, int rng, int fwdP, int chunk);
 DKernel pick_dupire_reverse(int prd);
+DKernel pick_dupire_reverse_quad(int prd);      // four lanes per live path (small shards)
 
 }  // namespace cf

@@ -23,12 +23,26 @@ plan = C.c_void_p()
 eng._chk(eng.lib.cf_plan_create(C.byref(mdl), C.byref(prd), C.byref(rg), C.byref(plan)))
 dout = torch.zeros(eng.lib.cf_plan_out_size(plan, 1), dtype=torch.float64, device="cuda")
 wv = (C.c_double * 2)(1.0, 0.0)
+stream = torch.cuda.Stream() if os.environ.get("CF_PROF_STREAM") else None
+sp = C.c_void_p(stream.cuda_stream) if stream else None
+first = int(os.environ.get("CF_PROF_FIRST", "0"))
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+step_ms = []
 for it in range(iters):
+    flush.fill_(it & 1)                     # L2 flush between iterations (untimed)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
     if mode == "aad":
-        eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, 0, N, dout.data_ptr(), None))
+        eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first, N, dout.data_ptr(), sp))
     else:
-        eng._chk(eng.lib.cf_plan_launch_value(plan, 0, N, dout.data_ptr(), None))
+        eng._chk(eng.lib.cf_plan_launch_value(plan, first, N, dout.data_ptr(), sp))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    step_ms.append(e0.elapsed_time(e1))
 torch.cuda.synchronize()
+step_ms = sorted(step_ms[2:]) if len(step_ms) > 4 else step_ms
+print("step ms (incl. reduction) median %.4f min %.4f" % (step_ms[len(step_ms) // 2], step_ms[0]), "sum %.17g" % float(dout[:4].sum().item()))
 ms = C.c_double(); nl = C.c_int()
 eng._chk(eng.lib.cf_plan_kernel_ms(plan, C.byref(ms), C.byref(nl)))
 print(mode, "kernel avg ms", ms.value, "paths/s %.4g" % (N / ms.value * 1e3), "fp64 peak TF", eng.fp64_peak_tflops())

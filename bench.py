@@ -10,8 +10,10 @@ pass.  Metric: paths/sec including the full AAD risk (whole job, all GPUs), fp64
   python bench.py --impl reference --gpus N ...             the reference's own CPU path (rank 0 only)
 
 N > 1 is STRONG scaling: the 2^20 paths are split into N disjoint skip-ahead blocks, one per rank
-(one process per GPU), and the payoff sums + adjoint vector (1084 doubles) are combined with one NCCL
-all-reduce per step, inside the timed region.
+(one process per GPU), and the payoff sums + adjoint vector (1084 doubles) are summed over the ranks inside
+the engine's final reduction kernel (peer memory over NVLink: cf_comm_create / cf_comm_connect, CUDA IPC
+handles gathered once with torch.distributed), inside the timed region; one NCCL all-reduce per step is the
+check and the fallback.
 """
 import argparse
 import ctypes as C
@@ -152,7 +154,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 1 << 18
+    sample = N_PATHS                       # the full job per step: the same configuration as the GPU arm
     for _ in range(max(args.warmup, 1)):
         cpu_reference_run(1 << 14)
     t_tot, pps = 0.0, []
@@ -164,8 +166,8 @@ def run_reference(args):
         "impl": "reference", "metric": "paths_per_sec_incl_full_aad_risk", "value": value, "unit": "paths/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU path (mcParallelSimulAAD via dupireAADRisk), "
-                   f"each step a bounded sample of {sample} paths of the same workload"},
+        "config": {"workload": WORKLOAD, "paths": N_PATHS, "steps_per_path": 156, "surface": "30x36", "rng": "sobol", "risks": 1081,
+                   "note": "reference CPU path (mcParallelSimulAAD via dupireAADRisk, oracle/_ref), each step the full 2^20-path job"},
         "cpu_baseline": {"value": value, "unit": "paths/s", "cores": threads, "kind": "reference",
                          "sample": f"{sample} paths x 156 steps per step, {args.steps} steps"},
         "e2e": {"value": value, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -227,25 +229,28 @@ def main():
     # checked once against one NCCL all-reduce of the per-rank results, which is also the fallback.
     fused = False
     if world > 1:
+        # reference result: per-rank launches, one NCCL all-reduce
+        eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first, count, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
+        dist.all_reduce(d_out)
+        want = d_out.clone()
+        ok_local = 1.0
         try:
-            from compfinance_b200.dist import PeerSum
-            peer = PeerSum(n_out)
-            eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first, count, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
-            dist.all_reduce(d_out)
-            want = d_out.clone()
-            peer.attach(eng.lib, plan)
+            from compfinance_b200.dist import connect_comm
+            connect_comm(eng, max(n_out, 4096))
             for _ in range(2):
                 eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first, count, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
             torch.cuda.synchronize()
-            okf = torch.tensor([1.0 if torch.allclose(d_out, want, rtol=1e-11, atol=1e-9) else 0.0], device="cuda")
-            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
-            fused = bool(okf.item() > 0.5)
-            if not fused:
-                peer.detach(eng.lib, plan)
-        except Exception as ex:                                   # symmetric memory unavailable: NCCL per step
+            ok_local = 1.0 if torch.allclose(d_out, want, rtol=1e-11, atol=1e-9) else 0.0
+        except Exception as ex:                                   # the blocks cannot be shared: NCCL per step
+            print(f"bench.py: rank {rank}: peer-memory reduction unavailable ({type(ex).__name__}: {ex})", file=sys.stderr)
+            ok_local = 0.0
+        okf = torch.tensor([ok_local], device="cuda")
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        fused = bool(okf.item() > 0.5)
+        if not fused:
+            eng.lib.cf_comm_enable(0)
             if rank == 0:
-                print(f"bench.py: peer-memory reduction unavailable ({type(ex).__name__}: {ex}); using NCCL", file=sys.stderr)
-            fused = False
+                print("bench.py: falling back to one NCCL all-reduce per step", file=sys.stderr)
 
     def step(first_path=first, n_paths=count):
         eng._chk(eng.lib.cf_plan_launch_aad(plan, wv, first_path, n_paths, d_out.data_ptr(), C.c_void_p(stream.cuda_stream)))
@@ -318,14 +323,19 @@ def main():
     d2h = int(n_out * 8)
 
     def e2e_step():
-        if world == 1:
+        # the call a user makes, on every rank: with the communicator connected the library runs this rank's shard of the
+        # 2^20 paths and the rank sum is part of its kernels; every rank returns the full result
+        if world == 1 or fused:
             return cf.dupire_aad_risk("bench_dupire", "bench_uoc", [1.0, 0.0], 30, 36, N_PATHS)
         r = eng.run_aad(mdl, prd, rng, first, count, [1.0, 0.0])          # C ABI, host buffers
         v = torch.from_numpy(np.concatenate([r["payoff_sums"], [r["agg_sum"]], r["table_adj"]])).pin_memory().cuda(non_blocking=True)
         dist.all_reduce(v)
         return v.cpu().numpy()
 
-    e2e_step()
+    e2e_res = e2e_step()
+    e2e_check = None
+    if isinstance(e2e_res, tuple):                                # (value, delta, vega) of dupireAADRisk: the same numbers as the device leg
+        e2e_check = {"price_rel_diff_vs_device_leg": abs(e2e_res[0] / price - 1), "delta_rel_diff_vs_device_leg": abs(e2e_res[1] / delta - 1)}
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -342,7 +352,15 @@ def main():
     clocks = sampler.stop()          # sampled under load: warm-up, timed region and the e2e loop
 
     if rank == 0:
-        fp64_peak = eng.fp64_peak_tflops()
+        # the roofline denominator, measured here with its own clock record: the DFMA microbenchmark is repeated for ~0.2 s
+        peak_sampler = ClockSampler(local_rank)
+        peak_sampler.start()
+        fp64_peak, t_end = 0.0, time.perf_counter() + 0.2
+        while time.perf_counter() < t_end:
+            fp64_peak = max(fp64_peak, eng.fp64_peak_tflops())
+        peak_clocks = peak_sampler.stop()
+        sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+        nominal_peak = 148 * 64 * 2 * sm_max * 1e6 / 1e12           # 148 SMs x 64 DFMA / clk x 2 flop at the maximum SM clock
         achieved = (count / (kms.value * 1e-3)) * FLOPS_PER_PATH / 1e12 if kms.value > 0 else None
         peaks = {}
         try:
@@ -358,10 +376,13 @@ def main():
         except OSError:
             pass
         roofline = {
-            "bound": "fp64", "kernel": "cf::dupire_forward4_kernel<UOC, AAD, Sobol, 2, 28> + cf::dupire_reverse_kernel<UOC> (one CUDA-event bracket around the pair)", "achieved": achieved, "peak": fp64_peak,
+            "bound": "fp64", "kernel": ("cf::dupire_forward4_kernel<UOC, AAD, Sobol, 2 paths / thread, 28 warps> + cf::dupire_reverse_kernel<UOC>" if count > 148 * 1536 else "cf::dupire_forward4_kernel<UOC, AAD, Sobol, 1 path / thread, 8-step chunks> + cf::dupire_reverse_span_kernel<UOC, 5> (programmatic dependent launch)") + " (one CUDA-event bracket around the pair)", "achieved": achieved, "peak": fp64_peak,
             "unit": "TFLOP/s", "frac": achieved / fp64_peak if achieved else None, "traffic": traffic,
             "kernel_ms": kms.value, "kernel_ms_per_rank": kms_per_rank, "kernel_launches_timed": kn.value,
-            "peak_source": "measured here: scalar DFMA microbenchmark cf_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 entry)",
+            "peak_source": "measured here: scalar DFMA microbenchmark cf_measure_fp64_peak, best of ~0.2 s of launches (MEASURED_PEAKS.json has no fp64 entry)",
+            "peak_clocks": peak_clocks, "peak_nominal": nominal_peak,
+            "peak_nominal_source": "148 SMs x 64 DFMA/clk x 2 flop x max SM clock", "frac_of_nominal": achieved / nominal_peak if achieved else None,
+            "traffic_source": "from_profile (profiles/latest_kernel.json: ncu --set full capture of one 2^20-path launch pair, not measured in this run)",
             "algorithmic_flops_per_path": FLOPS_PER_PATH,
             "hbm": {"achieved_gbs": (traffic / (kms.value * 1e-3) / 1e9) if traffic and kms.value > 0 else None,
                     "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json" if peaks else None},
@@ -384,7 +405,8 @@ def main():
                        "l2": "flushed between timed iterations (256 MB write)" + ("; ranks aligned by an untimed all-reduce after each flush" if world > 1 else ""), "price": price, "delta": delta},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d,
                                       "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                                      "api": "dupireAADRisk (libcf_host.so)" if world == 1 else "cf_run_aad (C ABI, host buffers) + NCCL all-reduce"},
+                                      "api": "dupireAADRisk (libcf_host.so)" if (world == 1 or fused) else "cf_run_aad (C ABI, host buffers) + NCCL all-reduce",
+                                      "value_check": e2e_check},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         if weak:

@@ -16,7 +16,7 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
 EXPORTED = [
-    "cfx_last_error", "cfx_init", "cfx_set_system_time", "cfx_put_black_scholes", "cfx_put_dupire",
+    "cfx_last_error", "cfx_init", "cfx_init_devices", "cfx_drop_sessions", "cfx_set_system_time", "cfx_put_black_scholes", "cfx_put_dupire",
     "cfx_put_european", "cfx_put_barrier", "cfx_put_contingent", "cfx_put_europeans", "cfx_put_displaced", "cfx_put_multistats",
     "cfx_put_baskets", "cfx_put_autocall", "cfx_num_payoffs", "cfx_num_params",
     "cfx_payoff_labels", "cfx_param_labels", "cfx_product_timeline", "cfx_value", "cfx_simul_paths",
@@ -37,13 +37,16 @@ def _d(a):
 class CompFinance:
     """Stateful facade: models and products live in the library's global stores (store.h semantics)."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, devices=None):
         if not os.path.exists(HOST_LIB_PATH):
             raise ImportError(f"{HOST_LIB_PATH} is missing: build it with `python -m compfinance_b200.build`")
         self.lib = C.CDLL(HOST_LIB_PATH)
         self.lib.cfx_last_error.restype = C.c_char_p
         self.lib.cfx_set_system_time.argtypes = [C.c_double]
-        if device is not None:
+        if devices is not None:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self._chk(self.lib.cfx_init_devices(C.c_int(len(devices)), ids))
+        elif device is not None:
             self._chk(self.lib.cfx_init(C.c_int(int(device))))
 
     def _chk(self, rc):

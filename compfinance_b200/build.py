@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcf_b200.so")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
-COMMON = ["cf_device.cuh", "cf_kernels.cuh", "cf_pick.h", os.path.join("..", "..", "include", "cf_b200.h")]
+COMMON = ["cf_device.cuh", "cf_comm.cuh", "cf_kernels.cuh", "cf_pick.h", os.path.join("..", "..", "include", "cf_b200.h")]
 # translation unit -> headers it depends on (besides COMMON); compiled in parallel, relinked when any object changes
 UNITS = {
     "cf_api.cu": ["cf_tables.h", "cf_dupire.cuh", "cf_dlm.cuh", "cf_multi.cuh"],

@@ -65,7 +65,15 @@ def load():
     lib.cf_plan_launch_value.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.cf_plan_launch_aad.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.cf_plan_kernel_ms.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int)]
-    lib.cf_plan_set_peers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.cf_plan_debug_times.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cf_plan_run_value.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _dp, _dp]
+    lib.cf_plan_run_aad.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, _dp]
+    lib.cf_plan_run_aad_multi.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _dp, _dp]
+    lib.cf_comm_create.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p]
+    lib.cf_comm_connect.argtypes = [C.c_void_p]
+    lib.cf_comm_enable.argtypes = [C.c_int]
+    lib.cf_comm_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.cf_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.cf_run_value.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product), C.POINTER(cf_rng), C.c_uint64,
                                  C.c_uint64, _dp, _dp]
     lib.cf_run_aad.argtypes = [C.POINTER(cf_model), C.POINTER(cf_product), C.POINTER(cf_rng), C.c_uint64,
@@ -83,7 +91,9 @@ def load():
 EXPORTED = [
     "cf_init", "cf_shutdown", "cf_last_error", "cf_launch_count", "cf_table_adjoint_size", "cf_run_value",
     "cf_run_aad", "cf_run_aad_multi", "cf_plan_create", "cf_plan_destroy", "cf_plan_launch_value", "cf_plan_launch_aad",
-    "cf_plan_out_size", "cf_plan_kernel_ms", "cf_plan_set_peers", "cf_sobol_states", "cf_sobol_direction_number", "cf_sobol_max_dim",
+    "cf_plan_out_size", "cf_plan_kernel_ms", "cf_plan_run_value", "cf_plan_run_aad", "cf_plan_run_aad_multi", "cf_plan_debug_times", "cf_device_count", "cf_context_generation",
+    "cf_comm_create", "cf_comm_connect", "cf_comm_enable", "cf_comm_destroy", "cf_comm_info", "cf_comm_status", "cf_shard_range",
+    "cf_sobol_states", "cf_sobol_direction_number", "cf_sobol_max_dim",
     "cf_rng_draw", "cf_mrg_numerators", "cf_inv_normal", "cf_measure_fp64_peak", "cf_device_sm_count",
 ]
 
@@ -95,12 +105,38 @@ class CfError(RuntimeError):
 class Engine:
     """Convenience wrapper over the C ABI taking numpy arrays."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, devices=None):
+        """device: one CUDA ordinal; devices: a list of ordinals -- a single-process multi-device context (runs are
+        sharded over them and summed over peer memory)."""
         self.lib = load()
         self._keep = []
-        if device is not None:
+        if devices is not None:
+            dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self._chk(self.lib.cf_init(len(devices), dev))
+        elif device is not None:
             dev = (C.c_int * 1)(int(device))
             self._chk(self.lib.cf_init(1, dev))
+
+    COMM_HANDLE_BYTES = 64
+
+    def comm_create(self, world, rank, capacity):
+        """This process's receive block of the rank sum; returns its CUDA IPC handle (bytes) for the launcher to gather."""
+        buf = C.create_string_buffer(self.COMM_HANDLE_BYTES)
+        self._chk(self.lib.cf_comm_create(world, rank, capacity, buf))
+        return buf.raw
+
+    def comm_connect(self, handles):
+        """handles: the participants' handles in rank order."""
+        blob = b"".join(handles)
+        self._chk(self.lib.cf_comm_connect(C.c_char_p(blob)))
+
+    def comm_enable(self, on):
+        self._chk(self.lib.cf_comm_enable(1 if on else 0))
+
+    def shard_range(self, n_paths, rank, world):
+        f, c = C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.cf_shard_range(n_paths, rank, world, C.byref(f), C.byref(c)))
+        return f.value, c.value
 
     def _chk(self, rc):
         if rc != 0:

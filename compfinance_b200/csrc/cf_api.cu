@@ -10,7 +10,11 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <condition_variable>
+#include <functional>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -26,8 +30,6 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
-int g_device = -1;
-int g_sms = 0;
 constexpr size_t kFastSmemLimit = 227 * 1024;   // opt-in shared memory per block on sm_100
 
 struct CfError : std::runtime_error { using std::runtime_error::runtime_error; };
@@ -57,18 +59,129 @@ void keep_pool_memory(int dev)
     }
 }
 
+// ---- the devices of the context (cf_init).  Device 0 of the list is driven by the calling thread; the others, if
+// any, by one worker thread each (launches on all devices are issued at the same time, not one device after the other).
+struct Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    std::atomic<int> state{0};            // 0 idle, 1 job posted, 2 job done, 3 quit
+    std::exception_ptr err;
+
+    template <class Pred> void spinThenWait(Pred done)
+    {
+        for (int i = 0; i < 20000 && !done(); ++i) { /* ~100 us of polling: a run is a fraction of a millisecond */ }
+        if (done()) return;
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, done);
+    }
+    void post(std::function<void()> f)
+    {
+        { std::lock_guard<std::mutex> lk(m); job = std::move(f); err = nullptr; state.store(1, std::memory_order_release); }
+        cv.notify_all();
+    }
+    void wait()
+    {
+        spinThenWait([&] { return state.load(std::memory_order_acquire) == 2; });
+        state.store(0, std::memory_order_release);
+        if (err) std::rethrow_exception(err);
+    }
+};
+
+struct DeviceCtx {
+    int id = -1, sms = 0, index = 0;      // CUDA ordinal, SM count, position in the context
+    cudaStream_t stream = nullptr;        // owned: host-buffer runs of a multi-device context
+    unsigned char* staging = nullptr;     // pinned block the table uploads of a plan are gathered in
+    cudaEvent_t copied = nullptr;         // the last batch has left the staging block
+    std::unique_ptr<Worker> worker;       // devices 1 .. n - 1
+};
+std::vector<std::unique_ptr<DeviceCtx>> g_devs;
+thread_local DeviceCtx* t_dev = nullptr;  // the device this thread is bound to
+int g_gen = 0;                            // bumped whenever the context is closed
+thread_local int t_gen = 0;
+#define g_sms (t_dev->sms)
+
+void bind(DeviceCtx* d)
+{
+    if (t_dev != d) { CF_CUDA(cudaSetDevice(d->id)); t_dev = d; }
+}
+// bind the calling thread to another device of the context for the lifetime of the scope
+struct DeviceScope {
+    DeviceCtx* prev;
+    explicit DeviceScope(DeviceCtx* d) : prev(t_dev) { bind(d); }
+    ~DeviceScope() { if (prev && prev != t_dev) { cudaSetDevice(prev->id); t_dev = prev; } }
+};
+
+void worker_main(DeviceCtx* d)
+{
+    Worker& w = *d->worker;
+    try { bind(d); } catch (...) { /* reported by the first job */ }
+    for (;;) {
+        w.spinThenWait([&] { const int s = w.state.load(std::memory_order_acquire); return s == 1 || s == 3; });
+        if (w.state.load(std::memory_order_acquire) == 3) return;
+        try { bind(d); w.job(); } catch (...) { w.err = std::current_exception(); }
+        { std::lock_guard<std::mutex> lk(w.m); w.state.store(2, std::memory_order_release); }
+        w.cv.notify_all();
+    }
+}
+
+std::unique_ptr<DeviceCtx> open_device(int id, int index, bool withWorker)
+{
+    auto d = std::make_unique<DeviceCtx>();
+    d->id = id; d->index = index;
+    CF_CUDA(cudaSetDevice(id));
+    CF_CUDA(cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, id));
+    keep_pool_memory(id);
+    if (withWorker) {
+        CF_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        if (index > 0) {
+            d->worker = std::make_unique<Worker>();
+            d->worker->th = std::thread(worker_main, d.get());
+        }
+    }
+    return d;
+}
+
+void retire_plans();     // the plans of the context go with it (defined after cf_plan)
+
+void close_devices()
+{
+    retire_plans();
+    for (auto& d : g_devs) {
+        if (d->worker) {
+            { std::lock_guard<std::mutex> lk(d->worker->m); d->worker->state.store(3); }
+            d->worker->cv.notify_all();
+            d->worker->th.join();
+        }
+        cudaSetDevice(d->id);
+        cudaDeviceSynchronize();
+        if (d->stream) cudaStreamDestroy(d->stream);
+        if (d->staging) cudaFreeHost(d->staging);
+        if (d->copied) cudaEventDestroy(d->copied);
+    }
+    g_devs.clear();
+    t_dev = nullptr;
+    ++g_gen;
+}
+
+// Binds the calling thread to device 0 of the context; without cf_init the context is the current CUDA device.
 void ensure_init()
 {
-    if (g_device >= 0) { CF_CUDA(cudaSetDevice(g_device)); return; }
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0)
-        throw CfError("cf_b200: no CUDA device available (this library has no CPU fallback)");
-    int dev = 0;
-    CF_CUDA(cudaGetDevice(&dev));
-    g_device = dev;
-    CF_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-    keep_pool_memory(dev);
+    if (g_devs.empty()) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw CfError("cf_b200: no CUDA device available (this library has no CPU fallback)");
+        int dev = 0;
+        CF_CUDA(cudaGetDevice(&dev));
+        g_devs.push_back(open_device(dev, 0, false));
+        t_dev = nullptr;
+        t_gen = g_gen;
+    }
+    if (t_gen != g_gen) { t_dev = nullptr; t_gen = g_gen; }          // the context has been re-created since this thread bound
+    if (!t_dev) bind(g_devs[0].get());
+    else CF_CUDA(cudaSetDevice(t_dev->id));                          // the caller may have changed the current device
 }
 
 // Table uploads of one plan are batched: while an UploadBatch is open, upload() copies the host data into a pinned
@@ -79,8 +192,8 @@ struct UploadBatch {
     unsigned char* dev = nullptr;       // device arena of this batch (owned by the plan)
     size_t used = 0;
     static UploadBatch*& current() { static thread_local UploadBatch* b = nullptr; return b; }
-    static unsigned char*& staging() { static unsigned char* h = nullptr; return h; }
-    static cudaEvent_t& copied() { static cudaEvent_t e = nullptr; return e; }
+    static unsigned char*& staging() { return t_dev->staging; }      // of the device this thread is bound to
+    static cudaEvent_t& copied() { return t_dev->copied; }
 };
 
 template <class T>
@@ -123,7 +236,7 @@ struct UploadScope {
     explicit UploadScope(DevBuf<unsigned char>& arena)
     {
         if (!UploadBatch::staging()) {
-            CF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&UploadBatch::staging()), UploadBatch::kCapacity, cudaHostAllocDefault));
+            CF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&UploadBatch::staging()), UploadBatch::kCapacity, cudaHostAllocPortable));
             CF_CUDA(cudaEventCreateWithFlags(&UploadBatch::copied(), cudaEventDisableTiming));
         } else {
             CF_CUDA(cudaEventSynchronize(UploadBatch::copied()));     // the previous batch has left the staging block
@@ -146,7 +259,7 @@ struct UploadScope {
 // stream (stream-ordered allocation: a buffer is only released after the work queued before it on that stream), never
 // shrunk.  A plan is used on one stream at a time; two plans never share scratch.
 struct Scratch {
-    DevBuf<double> hist, state, partial, partialRev, wtab, btab, tmp;
+    DevBuf<double> hist, state, partial, partialRev, wtab, btab, tmp, local;
     DevBuf<uint32_t> live;
     template <class T> void need(DevBuf<T>& b, size_t n, cudaStream_t s) { if (b.n < n) b.alloc(n, s); }
 };
@@ -239,19 +352,109 @@ void validate(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
     } else if (rng->kind != CF_RNG_MRG32K3A) throw CfError("cf_b200: unknown RNG kind");
 }
 
+// ---- the participants of the rank sum (cf_comm.cuh): the devices of this context, or one device per process
+struct CommState {
+    int world = 0;                        // participants, 0: no communicator
+    int rank0 = 0;                        // rank of local device 0 (local device k is participant rank0 + k)
+    size_t cap = 0;                       // doubles per row
+    bool enabled = false;                 // launches exchange (cf_comm_enable)
+    bool ipc = false;                     // participants are processes (CUDA IPC) rather than devices of this process
+    uint32_t epoch = 0;                   // exchanges so far, the same on every participant
+    long long timeout = 20000000000ll;    // clocks (~10 s) a participant waits for its peers
+    std::vector<unsigned char*> local;    // receive block of each local device (cudaMalloc)
+    std::vector<uint32_t*> ticket;        // per local device
+    std::vector<void*> opened;            // remote blocks opened through IPC
+    unsigned char* block[cf::kMaxPeers] = {};   // receive block of participant r as addressable from this process
+    int* status = nullptr;                // mapped pinned host word: epoch of an exchange that timed out, 0: none
+    int* statusDev = nullptr;
+
+    size_t rowBytes() const { return size_t(2) * size_t(world) * cap * sizeof(double); }
+    size_t blockBytes() const { return rowBytes() + 256; }
+    bool on() const { return world > 1 && enabled; }
+    cf::DPeers peers(int localIndex, uint32_t ep) const
+    {
+        cf::DPeers p{};
+        p.world = world; p.rank = rank0 + localIndex; p.epoch = ep; p.cap = cap; p.timeout = timeout;
+        for (int r = 0; r < world; ++r) {
+            p.buf[r] = reinterpret_cast<double*>(block[r]);
+            p.flag[r] = reinterpret_cast<uint32_t*>(block[r] + rowBytes());
+        }
+        p.ticket = ticket[size_t(localIndex)];
+        p.status = statusDev;
+        return p;
+    }
+    void check() const
+    {
+        if (status && *reinterpret_cast<volatile int*>(status) != 0)
+            throw CfError("cf_b200: a participant of the rank sum never arrived (exchange " + std::to_string(*status)
+                          + " timed out): results of that run are NaN");
+    }
+};
+CommState g_comm;
+
+void comm_destroy()
+{
+    for (auto& d : g_devs) { cudaSetDevice(d->id); cudaDeviceSynchronize(); }
+    for (void* q : g_comm.opened) cudaIpcCloseMemHandle(q);
+    for (size_t k = 0; k < g_comm.local.size(); ++k) {
+        if (k < g_devs.size()) cudaSetDevice(g_devs[k]->id);
+        if (g_comm.local[k]) cudaFree(g_comm.local[k]);
+        if (g_comm.ticket[k]) cudaFree(g_comm.ticket[k]);
+    }
+    if (g_comm.status) cudaFreeHost(g_comm.status);
+    g_comm = CommState{};
+    if (t_dev) cudaSetDevice(t_dev->id);
+}
+
+// receive blocks of the local devices (zeroed), tickets, the status word
+void comm_allocate(int world, int rank0, size_t cap)
+{
+    if (world < 2 || world > cf::kMaxPeers) throw CfError("cf_comm: the number of participants must be 2 .. 16");
+    if (cap == 0) throw CfError("cf_comm: zero capacity");
+    comm_destroy();
+    g_comm.world = world; g_comm.rank0 = rank0; g_comm.cap = cap;
+    CF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_comm.status), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *g_comm.status = 0;
+    CF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_comm.statusDev), g_comm.status, 0));
+    for (auto& d : g_devs) {
+        DeviceScope sc(d.get());
+        unsigned char* b = nullptr;
+        uint32_t* t = nullptr;
+        CF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b), g_comm.blockBytes()));
+        CF_CUDA(cudaMemset(b, 0, g_comm.blockBytes()));
+        CF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t), sizeof(uint32_t)));
+        CF_CUDA(cudaMemset(t, 0, sizeof(uint32_t)));
+        CF_CUDA(cudaDeviceSynchronize());
+        g_comm.local.push_back(b); g_comm.ticket.push_back(t);
+    }
+}
+
+// Shard of participant k of P over n paths: boundaries on multiples of 256 paths (one Sobol window) and even (an
+// antithetic pair of mrg32k3a is never split; the reference guarantees the same with its 64-path batches,
+// mcBase.h:312); the last participant takes the remainder.  Mirrors compfinance_b200/dist.py::shard_range.
+void shard_range(uint64_t n, int k, int P, uint64_t& first, uint64_t& count)
+{
+    uint64_t step = 256;
+    uint64_t per = (n / uint64_t(P)) / step * step;
+    if (per == 0) { step = 2; per = (n / uint64_t(P)) / step * step; }
+    first = uint64_t(k) * per;
+    count = k < P - 1 ? per : n - per * uint64_t(P - 1);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-struct cf_plan {
+// The plan of one device: tables resident in HBM, scratch, kernels.
+struct DevPlan {
+    DeviceCtx* dev = nullptr;             // the device the tables live on
+    DevBuf<double> outBuf, localBuf, perBuf, aggBuf;   // host-buffer runs: results (and local sums before the rank sum)
     int mdlKind = 0, prdKind = 0, rngKind = 0;
     int D = 0, m = 0, E = 0, dim = 0, nPay = 0;
     size_t nAdj = 0;           // table adjoints including the spot leaf
     DevBuf<unsigned char> arena;      // one device block for all the tables uploaded by make_plan
-    cf::DPeers peers{};               // multi-GPU: the peers' result buffers and flags (cf_plan_set_peers), world = 0: none
-    uint32_t peerEpoch = 0;
-    DevBuf<uint32_t> peerTicket;
     bool tablesInFlight = true;       // the first launch orders its stream after the table upload (null stream)
     Scratch scratch;
+    DevBuf<unsigned long long> dbgTimes;    // CF_DEBUG_TIMES: phase stamps of the Dupire kernels (cf_plan_debug_times)
     cf::KArgs base{};
     DevBuf<uint8_t> isEvent;
     DevBuf<double> tabA, tabB, num, ff, disc, libors, eventDt;
@@ -269,6 +472,9 @@ struct cf_plan {
     DevBuf<uint32_t> stepBits;
     DevBuf<int32_t> k12;
     DevBuf<uint8_t> flushOps;
+    DevBuf<double2> spanW;            // span reverse kernel: per step time weights, packed columns / phases, phases per round
+    DevBuf<uint32_t> spanPack, spanNph;
+    int spanS = 0;                    // steps per lane; 0: the span kernel cannot run this plan
     int nCells = 0;
     cf::DArgs dbase{};
     // displaced multi-asset model (cf_dlm.cuh)
@@ -282,7 +488,7 @@ struct cf_plan {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // recorded since last query
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
 
-    ~cf_plan()
+    ~DevPlan()
     {
         for (auto& e : events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto& e : pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -293,14 +499,37 @@ struct cf_plan {
     std::pair<cudaEvent_t, cudaEvent_t> takeEvents()
     {
         std::pair<cudaEvent_t, cudaEvent_t> ev;
+        if (events.size() >= 256) {       // nobody polls cf_plan_kernel_ms: recycle the oldest pair instead of growing
+            pool.push_back(events.front());
+            events.erase(events.begin());
+        }
         if (!pool.empty()) { ev = pool.back(); pool.pop_back(); }
         else { CF_CUDA(cudaEventCreate(&ev.first)); CF_CUDA(cudaEventCreate(&ev.second)); }
         return ev;
     }
 
-    void launch(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut, double* dPerPath,
-                double* dPerAgg, cudaStream_t s)
+    // The sum over participants of a result vector already reduced on this device (generic paths; the Dupire fast path
+    // does it inside its own reduction kernel).
+    void exchange(const double* dLocal, int nOut, double* dOut, const cf::DPeers& px, cudaStream_t s)
     {
+        if (size_t(nOut) > px.cap) throw CfError("cf_b200: result vector longer than the communicator's capacity");
+        const int block = 256, grid = std::max(1, std::min(dev->sms, (nOut + block - 1) / block));
+        cf::peer_exchange_kernel<<<grid, block, 0, s>>>(dLocal, nOut, dOut, px);
+        CF_CUDA(cudaGetLastError());
+        ++g_launches;
+    }
+
+    // px: the participants of the rank sum, or null (single GPU, or the caller reduces)
+    void launch(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut, double* dPerPath,
+                double* dPerAgg, cudaStream_t s, const cf::DPeers* px = nullptr)
+    {
+        if (px && n == 0) {               // a participant without paths still takes part in the exchange
+            const int nOut = int(outSize(aad));
+            scratch.need(scratch.tmp, size_t(nOut), s);
+            CF_CUDA(cudaMemsetAsync(scratch.tmp.p, 0, sizeof(double) * size_t(nOut), s));
+            exchange(scratch.tmp.p, nOut, dOut, *px, s);
+            return;
+        }
         if (n == 0) throw CfError("cf_b200: n_paths must be > 0");
         if (rngKind == CF_RNG_SOBOL && first + n > 0xffffffffull) throw CfError("cf_b200: Sobol index exceeds 2^32 - 1");
         // the reference's skipTo takes an unsigned path index (mrg32k3a.h:192); the jump matrices cover 32 bits of pair index
@@ -312,8 +541,8 @@ struct cf_plan {
         const uint64_t nb64 = (n + cf::kBlock - 1) / cf::kBlock;
         if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
         const int nBatches = int(nb64);
-        if (mdlKind == CF_MODEL_DISPLACED) { launchDlm(aad, w, first, n, nBatches, dOut, dPerPath, dPerAgg, s); return; }
-        if (fast && (!aad || hasTimeMap)) { launchFast(aad, w, first, n, dOut, dPerPath, dPerAgg, s); return; }
+        if (mdlKind == CF_MODEL_DISPLACED) { launchDlm(aad, w, first, n, nBatches, dOut, dPerPath, dPerAgg, s, px); return; }
+        if (fast && (!aad || hasTimeMap)) { launchFast(aad, w, first, n, dOut, dPerPath, dPerAgg, s, px); return; }
 
         const int grid = std::min(nBatches, 2 * g_sms);
         const size_t tabAdj = mdlKind == CF_MODEL_DUPIRE ? 1 + size_t(D) * m : nAdj;   // generic kernel: table adjoints
@@ -349,25 +578,27 @@ struct cf_plan {
         CF_CUDA(cudaEventRecord(ev.second, s));
         events.push_back(ev);
         CF_CUDA(cudaGetLastError());
+        const int nOutAll = int(outSize(aad));
+        double* dLocal = dOut;
+        if (px) { scratch.need(scratch.local, size_t(nOutAll), s); dLocal = scratch.local.p; }
         if (aad && mdlKind == CF_MODEL_DUPIRE && hasTimeMap) {
             // generic kernel produced interp_vols adjoints: reduce, then apply the time map
             scratch.need(scratch.tmp, stride, s);
             cf::reduce_partials_kernel<<<(int(stride) + 127) / 128, 128, 0, s>>>(scratch.partial.p, grid, partialStride, int(stride), scratch.tmp.p);
-            const int nOut = int(outSize(true));
-            cf::collapse_time_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(scratch.tmp.p, nPay + 2, D, m, nTimes, tk1.p, tk2.p, tc1.p, tc2.p, dOut);
+            cf::collapse_time_kernel<<<(nOutAll + 127) / 128, 128, 0, s>>>(scratch.tmp.p, nPay + 2, D, m, nTimes, tk1.p, tk2.p, tc1.p, tc2.p, dLocal);
             g_launches += 1;
         } else {
-            const int nOut = int(outSize(aad));
-            cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(scratch.partial.p, grid, partialStride, nOut, dOut);
+            cf::reduce_partials_kernel<<<(nOutAll + 127) / 128, 128, 0, s>>>(scratch.partial.p, grid, partialStride, nOutAll, dLocal);
         }
         CF_CUDA(cudaGetLastError());
         g_launches += 2;
+        if (px) exchange(dLocal, nOutAll, dOut, *px, s);
     }
 
     using LKernel = cf::LKernel;
 
     void launchDlm(bool aad, const double* w, uint64_t first, uint64_t n, int nBatches, double* dOut, double* dPerPath,
-                   double* dPerAgg, cudaStream_t s)
+                   double* dPerAgg, cudaStream_t s, const cf::DPeers* px)
     {
         const int grid = std::min(nBatches, 2 * g_sms);
         const size_t stride = aad ? size_t(nPay) + 1 + nAdj : size_t(nPay);
@@ -396,9 +627,12 @@ struct cf_plan {
         events.push_back(ev);
         CF_CUDA(cudaGetLastError());
         const int nOut = int(outSize(aad));
-        cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(scratch.partial.p, grid, partialStride, nOut, dOut);
+        double* dLocal = dOut;
+        if (px) { scratch.need(scratch.local, size_t(nOut), s); dLocal = scratch.local.p; }
+        cf::reduce_partials_kernel<<<(nOut + 127) / 128, 128, 0, s>>>(scratch.partial.p, grid, partialStride, nOut, dLocal);
         CF_CUDA(cudaGetLastError());
         g_launches += 2;
+        if (px) exchange(dLocal, nOut, dOut, *px, s);
     }
 
     using DKernel = cf::DKernel;
@@ -416,16 +650,95 @@ struct cf_plan {
     // n_steps * 8 bytes per path (1.3 GB for 2^20 paths x 156 steps).
     static constexpr uint64_t kFastChunk = 1ull << 21;
 
-    // The reverse sweep has two forms (cf_dupire.cuh): one path per lane, 8 warps (many live paths per SM), and four
-    // lanes per path, 16 warps (few: a shard of a multi-GPU run).  CF_DUPIRE_REV = quad | classic forces one.
-    bool reverseQuad(uint64_t nPad) const
+    // ---- itemised risk of Dupire x Europeans (cf_multi.cuh): strikes sorted per event, classes, result maps
+    bool multiReady = false;
+    int multiCmax = 1;
+    double spot0 = 0.0;
+    DevBuf<double> mK;
+    DevBuf<int32_t> mEvent, mRank, mOrig;
+    DevBuf<long long> mThi, mTlo;
+    DevBuf<double> mT, mPartial, mSums;
+
+    size_t multiOutSize() const { return size_t(nPay) + nAdj * size_t(nPay); }
+
+    // dOut: [n_payoffs] payoff sums, then [nAdj][n_payoffs] sums over paths of d payoff / d table
+    void launchMulti(uint64_t first, uint64_t n, double* dOut, cudaStream_t s, const cf::DPeers* px)
+    {
+        if (!multiReady) throw CfError("cf_b200: this plan has no strike-class kernel");
+        const size_t nOutAll = multiOutSize();
+        double* dLocal = dOut;
+        if (px) { scratch.need(scratch.local, nOutAll, s); dLocal = scratch.local.p; }
+        if (px && n == 0) {
+            CF_CUDA(cudaMemsetAsync(dLocal, 0, sizeof(double) * nOutAll, s));
+            exchange(dLocal, int(nOutAll), dOut, *px, s);
+            return;
+        }
+        if (n == 0) throw CfError("cf_b200: n_paths must be > 0");
+        if (rngKind == CF_RNG_SOBOL && first + n > 0xffffffffull) throw CfError("cf_b200: Sobol index exceeds 2^32 - 1");
+        if (rngKind != CF_RNG_SOBOL && first + n > (1ull << 32)) throw CfError("cf_b200: mrg32k3a path index exceeds 2^32 - 1");
+        if (tablesInFlight) {
+            if (UploadBatch::copied()) CF_CUDA(cudaStreamWaitEvent(s, UploadBatch::copied(), 0));
+            tablesInFlight = false;
+        }
+        const size_t tabLen = 1 + size_t(D) * m;
+        const size_t tSize = size_t(E) * multiCmax * tabLen;
+        if (mThi.n < tSize) { mThi.alloc(tSize, s); mTlo.alloc(tSize, s); mT.alloc(tSize, s); }
+        CF_CUDA(cudaMemsetAsync(mThi.p, 0, sizeof(long long) * tSize, s));
+        CF_CUDA(cudaMemsetAsync(mTlo.p, 0, sizeof(long long) * tSize, s));
+        const uint64_t nb64 = (n + cf::kBlock - 1) / cf::kBlock;
+        if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
+        const int grid = int(std::min<uint64_t>(nb64, uint64_t(2) * dev->sms));
+        if (mPartial.n < size_t(grid) * nPay) mPartial.alloc(size_t(grid) * nPay, s);
+        if (mSums.n < size_t(nPay)) mSums.alloc(size_t(nPay), s);
+        // fixed point of the remainders: |lo| <= 2^-11 per addend, n addends: 2^(lo_bits - 11) n < 2^62
+        int loBits = 50;
+        while (loBits > 20 && std::ldexp(double(n), loBits - 11) >= std::ldexp(1.0, 62)) --loBits;
+        // the coarse part: |x| 2^10 n < 2^62 with |x| up to ~ 2^10 spot
+        if (std::ldexp(double(n) * std::fabs(spot0), 20) >= std::ldexp(1.0, 62)) throw CfError("cf_b200: spot x paths too large for the fixed-point accumulators of the itemised risk");
+        cf::MArgs a{};
+        a.first_path = first; a.n_paths = n; a.n_batches = int(nb64);
+        a.seed1 = base.seed1; a.seed2 = base.seed2; a.dim = dim;
+        a.sobol_dir = sobolDir.p; a.mrg_jump = mrgJump.p;
+        a.D = D; a.m = m; a.E = E; a.is_event = isEvent.p; a.spot = spot0;
+        a.interp_vols = tabA.p; a.log_spots = tabB.p;
+        a.ksorted = mK.p; a.koff = eOff.p; a.n_payoffs = nPay; a.cmax = multiCmax;
+        a.partial = mPartial.p; a.Thi = mThi.p; a.Tlo = mTlo.p; a.lo_scale = std::ldexp(1.0, loBits); a.per_path_payoffs = nullptr;
+        const bool sob = rngKind == CF_RNG_SOBOL;
+        const size_t smem = cf::multi_smem(D, m, nPay, dim, sob).total;
+        if (smem > kFastSmemLimit / 2) throw CfError("cf_run_aad_multi: tables do not fit in shared memory");
+        auto fn = cf::pick_multi_kernel(rngKind);
+        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        auto ev = takeEvents();
+        CF_CUDA(cudaEventRecord(ev.first, s));
+        fn<<<grid, cf::kBlock, smem, s>>>(a);
+        CF_CUDA(cudaEventRecord(ev.second, s));
+        events.push_back(ev);
+        CF_CUDA(cudaGetLastError());
+        cf::reduce_partials_kernel<<<(nPay + 127) / 128, 128, 0, s>>>(mPartial.p, grid, nPay, nPay, mSums.p);
+        cf::multi_unsort_kernel<<<(nPay + 127) / 128, 128, 0, s>>>(mSums.p, mOrig.p, nPay, dLocal);
+        const size_t nSuffix = size_t(E) * tabLen;
+        cf::multi_suffix_kernel<<<unsigned((nSuffix + 255) / 256), 256, 0, s>>>(mThi.p, mTlo.p, std::ldexp(1.0, -loBits), mT.p, E, multiCmax, tabLen);
+        const size_t nParam = 1 + size_t(m) * nTimes;
+        cf::multi_collapse_kernel<<<unsigned((nParam * nPay + 255) / 256), 256, 0, s>>>(mT.p, E, multiCmax, D, m, nTimes, tk1.p, tk2.p, tc1.p, tc2.p,
+                                                                                       mEvent.p, mRank.p, mOrig.p, nPay, dLocal + nPay);
+        CF_CUDA(cudaGetLastError());
+        g_launches += 5;
+        if (px) exchange(dLocal, int(nOutAll), dOut, *px, s);
+    }
+
+    // The reverse sweep has two forms (cf_dupire.cuh): classic (one path per lane, 8 warps: many live paths per SM) and
+    // span (one warp per live path, a lane per S consecutive steps, 16 warps: few live paths per SM, the shard of a
+    // multi-GPU run).  Measured cross-over: about 1500 paths per SM.  CF_DUPIRE_REV = span | classic forces one.
+    enum { kRevSpan = 0, kRevClassic = 2 };
+    int reverseForm(uint64_t nPad) const
     {
         static const int forced = [] {
             const char* e = std::getenv("CF_DUPIRE_REV");
-            return !e ? 0 : (std::strcmp(e, "quad") == 0 ? 1 : (std::strcmp(e, "classic") == 0 ? 2 : 0));
+            return !e ? -1 : (std::strcmp(e, "classic") == 0 ? int(kRevClassic) : (std::strcmp(e, "span") == 0 ? int(kRevSpan) : -1));
         }();
-        if (forced) return forced == 1;
-        return nPad <= uint64_t(g_sms) * 2048;
+        int form = forced >= 0 ? forced : (nPad <= uint64_t(g_sms) * 1536 ? int(kRevSpan) : int(kRevClassic));
+        if (form == kRevSpan && spanS == 0) form = kRevClassic;
+        return form;
     }
 
     // kernel launch on stream s, optionally with programmatic stream serialization (the kernel may start while its
@@ -443,7 +756,7 @@ struct cf_plan {
     }
 
     void launchFast(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut,
-                    double* dPerPath, double* dPerAgg, cudaStream_t s)
+                    double* dPerPath, double* dPerAgg, cudaStream_t s, const cf::DPeers* px)
     {
         static const bool pdl = [] { const char* e = std::getenv("CF_PDL"); return !e || std::atoi(e) != 0; }();
         const bool sob = rngKind == CF_RNG_SOBOL;
@@ -454,8 +767,10 @@ struct cf_plan {
         const uint64_t maxPad = (maxChunk + quantum - 1) / quantum * quantum;
         const int maxUnitsF = int(maxPad / quantum) * 8;
         const int gridF = std::min(maxUnitsF, g_sms);       // units are dealt round-robin: small runs still use every SM
-        const bool quad = aad && reverseQuad(maxPad);
-        const int revWarps = quad ? cf::kRevQWarps : cf::kRevWarps, revMaxWords = quad ? cf::kRevQMaxWords : cf::kRevMaxWords;
+        const int form = reverseForm(maxPad);
+        const bool span = form == kRevSpan;
+        const int revWarps = span ? cf::kRevSWarps : cf::kRevWarps;
+        const int revMaxWords = span ? cf::kRevSMaxWords : cf::kRevMaxWords;
         // reverse blocks own contiguous ranges of live-mask words (32 paths each), at most revMaxWords per block
         const int minGridR = int((maxPad / 32 + revMaxWords - 1) / revMaxWords);
         const int gridR = std::max(int(std::min<uint64_t>(maxPad / 32, uint64_t(g_sms))), minGridR);
@@ -466,7 +781,7 @@ struct cf_plan {
             scratch.need(scratch.state, 2 * maxPad, s);
             scratch.need(scratch.live, size_t(maxPad / 32), s);
             scratch.need(scratch.partialRev, size_t(gridR), s);
-            scratch.need(scratch.wtab, size_t(gridR) * revWarps * tabLen, s);
+            if (!span) scratch.need(scratch.wtab, size_t(gridR) * revWarps * tabLen, s);
             scratch.need(scratch.btab, size_t(gridR) * tabLen, s);
         }
         DKernel fwd;
@@ -477,10 +792,12 @@ struct cf_plan {
         smemF = fwdP == 2 ? cf::dupire_smem_fwd4<2, cf::kFwdChunk>(D, m, dim, sob, nCells, fwdWarps).total
               : fwdCh == cf::kFwdChunk ? cf::dupire_smem_fwd4<1, cf::kFwdChunk>(D, m, dim, sob, nCells, fwdWarps).total
                                        : cf::dupire_smem_fwd4<1, cf::kFwdChunk1>(D, m, dim, sob, nCells, fwdWarps).total;
-        auto rev = quad ? cf::pick_dupire_reverse_quad(prdKind) : cf::pick_dupire_reverse(prdKind);
-        const size_t smemR = quad ? cf::dupire_smem_revq(D, m, nCells).total : cf::dupire_smem_rev(D, m, nCells).total;
+        auto rev = span ? cf::pick_dupire_reverse_span(prdKind, spanS) : cf::pick_dupire_reverse(prdKind);
+        const size_t smemR = span ? cf::dupire_smem_revs(D, m, nCells, nTimes).total : cf::dupire_smem_rev(D, m, nCells).total;
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fwd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
         if (aad) CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rev), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemR)));
+        static const bool dbgT = std::getenv("CF_DEBUG_TIMES") != nullptr;
+        if (dbgT && !dbgTimes.p) { dbgTimes.alloc(3 * 1024 * 8, s); CF_CUDA(cudaMemsetAsync(dbgTimes.p, 0, 3 * 1024 * 8 * 8, s)); }
         auto ev = takeEvents();
         CF_CUDA(cudaEventRecord(ev.first, s));
         for (uint64_t off = 0; off < n; off += kFastChunk) {
@@ -496,37 +813,46 @@ struct cf_plan {
             a.per_path_payoffs = dPerPath ? dPerPath + off * nPay : nullptr;
             a.per_path_agg = dPerAgg ? dPerAgg + off : nullptr;
             a.n_units = int(a.n_pad / quantum) * 8;
+            a.dbg = dbgTimes.p;
             launchKernel(fwd, gridF, fwdWarps * 32, smemF, s, a, false);
             ++g_launches;
             if (aad) {
-                launchKernel(rev, gridR, revWarps * 32, smemR, s, a, pdl && quad);
+                launchKernel(rev, gridR, revWarps * 32, smemR, s, a, pdl);
                 ++g_launches;
             }
         }
         CF_CUDA(cudaEventRecord(ev.second, s));
         events.push_back(ev);
         const int nOut = int(outSize(aad));
-        cf::DPeers pr = peers;
-        if (pr.world > 1) {
-            if (pr.world > cf::kMaxPeers) throw CfError("cf_b200: too many peers");
-            pr.epoch = ++peerEpoch;
-            if (!peerTicket.p) { peerTicket.alloc(1); CF_CUDA(cudaMemsetAsync(peerTicket.p, 0, sizeof(uint32_t), s)); }
-            pr.ticket = peerTicket.p;
+        cf::DPeers pr{};
+        if (px) {
+            if (size_t(nOut) > px->cap) throw CfError("cf_b200: result vector longer than the communicator's capacity");
+            pr = *px;
         }
-        cf::dupire_reduce_kernel<<<(nOut * 32 + 255) / 256, 256, 0, s>>>(scratch.partial.p, gridF, nPay, scratch.partialRev.p,
-                                                                        scratch.btab.p, gridR, m, nTimes, aad ? 1 : 0, dOut, pr);
-        CF_CUDA(cudaGetLastError());
+        {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(unsigned((nOut * 32 + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = (pdl && aad) ? 1 : 0;
+            const double* cPartial = scratch.partial.p; const double* cRev = scratch.partialRev.p; const double* cBtab = scratch.btab.p;
+            CF_CUDA(cudaLaunchKernelEx(&cfg, cf::dupire_reduce_kernel, cPartial, gridF, nPay, cRev, cBtab, gridR, m, nTimes,
+                                       aad ? 1 : 0, dOut, pr));
+        }
         ++g_launches;
     }
 };
 
 namespace {
 
-std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
+std::unique_ptr<DevPlan> make_plan(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
 {
     ensure_init();
     validate(mdl, prd, rng);
-    auto p = std::make_unique<cf_plan>();
+    auto p = std::make_unique<DevPlan>();
+    p->dev = t_dev;
+    p->spot0 = mdl->spot;
     UploadScope uploads(p->arena);
     p->mdlKind = mdl->kind; p->prdKind = prd->kind; p->rngKind = rng->kind;
     p->D = mdl->n_steps; p->E = mdl->n_events; p->dim = mdl->n_steps * mdl->n_assets;
@@ -717,11 +1043,53 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 p->c12.upload(wxy.data(), wxy.size());
                 p->k12.upload(colxy.data(), colxy.size());
                 p->flushOps.upload(ops.data(), ops.size());
+                // span reverse kernel: lane l sweeps steps [S l, S l + S); in round j the 32 lanes add to the time columns of
+                // steps S l + j.  Targets (step, column) get a phase such that no column is touched twice in a phase of a round.
+                {
+                    const int S = cf::dupire_span_steps(D);
+                    std::vector<double2> sw(static_cast<size_t>(D));
+                    std::vector<uint32_t> pack(static_cast<size_t>(D), 0u), nph(8, 1u);
+                    bool ok = S > 0 && p->hasTimeMap && p->nTimes <= 255
+                              && cf::dupire_smem_revs(D, m, nCells, p->nTimes).total <= kFastSmemLimit;
+                    for (int j = 0; ok && j < S; ++j) {
+                        std::vector<std::vector<int>> used(cf::kRevSMaxPhases);
+                        auto place = [&](int col, int notPhase) {
+                            for (int ph = 0; ph < cf::kRevSMaxPhases; ++ph)
+                                if (ph != notPhase && std::find(used[size_t(ph)].begin(), used[size_t(ph)].end(), col) == used[size_t(ph)].end()) {
+                                    used[size_t(ph)].push_back(col);
+                                    return ph;
+                                }
+                            return -1;
+                        };
+                        int phases = 1;
+                        for (int l = 0; l < 32 && ok; ++l) {
+                            const int i = S * l + j;
+                            if (i >= D) break;
+                            int c1 = mdl->time_col1[i], c2 = mdl->time_col2[i];
+                            double v1 = mdl->time_w1[i], v2 = mdl->time_w2[i];
+                            if (c2 == c1) { v1 += v2; v2 = 0.0; }
+                            const bool has2 = v2 != 0.0;
+                            const int ph1 = place(c1, -1), ph2 = has2 ? place(c2, ph1) : 0;     // a step's two targets never share a phase
+                            if (ph1 < 0 || ph2 < 0) { ok = false; break; }
+                            phases = std::max(phases, std::max(ph1, ph2) + 1);
+                            sw[size_t(i)] = make_double2(v1, v2);
+                            pack[size_t(i)] = uint32_t(c1) | (uint32_t(has2 ? c2 : c1) << 8) | (uint32_t(ph1) << 16) | (uint32_t(ph2) << 18)
+                                              | (has2 ? cf::DSpanStep::kHas2 : 0u)
+                                              | ((i + 1 < D && mdl->is_event[i + 1]) ? cf::DSpanStep::kEvent : 0u);
+                        }
+                        nph[size_t(j)] = uint32_t(phases);
+                    }
+                    if (ok) {
+                        p->spanS = S;
+                        p->spanW.upload(sw.data(), sw.size());
+                        p->spanPack.upload(pack.data(), pack.size());
+                        p->spanNph.upload(nph.data(), nph.size());
+                    }
+                }
                     const bool sob = rng->kind == CF_RNG_SOBOL;
                 if (cf::dupire_smem_fwd4<2, cf::kFwdChunk>(D, m, p->dim, sob, nCells, cf::kFwdWarps).total > kFastSmemLimit
                     || cf::dupire_smem_fwd4<1, cf::kFwdChunk1>(D, m, p->dim, sob, nCells, cf::kFwdWarps).total > kFastSmemLimit
-                    || cf::dupire_smem_rev(D, m, nCells).total > kFastSmemLimit
-                    || cf::dupire_smem_revq(D, m, nCells).total > kFastSmemLimit) p->fast = false;
+                    || cf::dupire_smem_rev(D, m, nCells).total > kFastSmemLimit) p->fast = false;
                 // Moro's branch test |u - 1/2| < 0.42 (gaussians.h:54) as a range of the RNG integer z: u(z) is
                 // monotone, so the central set is an interval [lo, hi]; searched with the device's own arithmetic
                 // (u = c z for Sobol, z / (m1 + 1) for mrg32k3a; u - 1/2 is exact on both sides of 1/2)
@@ -747,6 +1115,7 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 d.ab = p->ab.p; d.yrows = p->tabA.p; d.bk = p->bk.p; d.cells = p->cells.p; d.n_cells = nCells;
                 d.cell_scale = scale; d.cell_off = -x0 * scale;
                 d.wxy = p->c12.p; d.colxy = p->k12.p; d.flush_ops = p->flushOps.p;
+                d.span_w = p->spanW.p; d.span_pack = p->spanPack.p; d.span_nph = p->spanNph.p; d.span_S = p->spanS;
                 d.n_payoffs = prd->n_payoffs; d.is_put = prd->is_put;
                 d.strike = prd->strike; d.barrier = prd->barrier; d.smooth = prd->smooth;
             }
@@ -756,6 +1125,35 @@ std::unique_ptr<cf_plan> make_plan(const cf_model* mdl, const cf_product* prd, c
     a.strike = prd->strike; a.barrier = prd->barrier; a.smooth = prd->smooth; a.coupon = prd->coupon; a.event_dt = p->eventDt.p;
     a.strikes = p->eStrikes.p; a.strike_off = p->eOff.p;
     if (prd->kind == CF_PRODUCT_EUROPEANS) p->fast = false;      // many payoffs: generic kernel
+    if (mdl->kind == CF_MODEL_DUPIRE && prd->kind == CF_PRODUCT_EUROPEANS && p->hasTimeMap && p->D <= cf::kMultiMaxSteps) {
+        // itemised risk by strike class (cf_multi.cuh): strikes ascending within each event
+        const int nPay = p->nPay, E = p->E;
+        std::vector<double> ksorted(static_cast<size_t>(nPay));
+        std::vector<int32_t> payEvent(static_cast<size_t>(nPay)), payRank(static_cast<size_t>(nPay)), payOrig(static_cast<size_t>(nPay));
+        int cmax = 1;
+        for (int e = 0; e < E; ++e) {
+            const int k0 = prd->strike_offsets[e], k1 = prd->strike_offsets[e + 1];
+            std::vector<int> order;
+            for (int k = k0; k < k1; ++k) order.push_back(k);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return prd->strikes[x] < prd->strikes[y]; });
+            for (int r = 0; r < k1 - k0; ++r) {
+                ksorted[size_t(k0 + r)] = prd->strikes[order[size_t(r)]];
+                payEvent[size_t(k0 + r)] = e; payOrig[size_t(k0 + r)] = order[size_t(r)];
+            }
+            // class of a path = #strikes strictly below S_e; a payoff is in the money for the classes above the position
+            // of the LAST strike equal to its own
+            for (int r = 0; r < k1 - k0; ++r) {
+                int last = r;
+                while (last + 1 < k1 - k0 && ksorted[size_t(k0 + last + 1)] == ksorted[size_t(k0 + r)]) ++last;
+                payRank[size_t(k0 + r)] = last;
+            }
+            cmax = std::max(cmax, k1 - k0 + 1);
+        }
+        p->multiCmax = cmax;
+        p->mK.upload(ksorted.data(), ksorted.size());
+        p->mEvent.upload(payEvent.data(), payEvent.size()); p->mRank.upload(payRank.data(), payRank.size()); p->mOrig.upload(payOrig.data(), payOrig.size());
+        p->multiReady = true;
+    }
     uploads.close();
     return p;
 }
@@ -896,6 +1294,131 @@ void rng_run(const cf_rng* rng, int dim, uint64_t first, uint64_t n, int gaussia
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// The public plan: one DevPlan per device of the context.
+struct cf_plan;
+namespace { std::vector<cf_plan*>& live_plans() { static std::vector<cf_plan*> v; return v; } }
+
+struct cf_plan {
+    std::vector<std::unique_ptr<DevPlan>> dev;   // empty once the context the plan was created in has been closed
+    double* hostOut = nullptr;            // pinned staging of the results of host-buffer runs
+    size_t hostCap = 0;
+
+    cf_plan() { live_plans().push_back(this); }
+    DevPlan& d0()
+    {
+        if (dev.empty()) throw CfError("cf_b200: this plan belongs to a context that has been closed (cf_init / cf_shutdown)");
+        return *dev[0];
+    }
+    const DevPlan& d0() const { return const_cast<cf_plan*>(this)->d0(); }
+    // frees the device side (tables, scratch) on the devices it lives on
+    void retire()
+    {
+        for (auto& p : dev) {
+            if (!p) continue;
+            cudaSetDevice(p->dev->id);
+            cudaDeviceSynchronize();      // launches may be in flight on the caller's streams; the tables go back to the pool
+            p.reset();
+        }
+        dev.clear();
+    }
+    double* pinned(size_t n)
+    {
+        if (hostCap < n) {
+            if (hostOut) cudaFreeHost(hostOut);
+            hostOut = nullptr; hostCap = 0;
+            CF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&hostOut), n * sizeof(double), cudaHostAllocPortable));
+            hostCap = n;
+        }
+        return hostOut;
+    }
+    ~cf_plan()
+    {
+        retire();
+        if (hostOut) cudaFreeHost(hostOut);
+        if (t_dev) cudaSetDevice(t_dev->id);
+        auto& v = live_plans();
+        v.erase(std::remove(v.begin(), v.end(), this), v.end());
+    }
+};
+
+namespace {
+
+void retire_plans() { for (cf_plan* p : live_plans()) p->retire(); }
+
+std::unique_ptr<cf_plan> make_multi_plan(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
+{
+    ensure_init();
+    auto mp = std::make_unique<cf_plan>();
+    for (auto& d : g_devs) {
+        DeviceScope sc(d.get());
+        mp->dev.push_back(make_plan(mdl, prd, rng));
+    }
+    return mp;
+}
+
+// Runs `job(k)` for the local devices k < nLocal at the same time: device 0 on the calling thread, the others on
+// their worker threads.
+template <class F>
+void on_devices(int nLocal, F&& job)
+{
+    for (int k = 1; k < nLocal; ++k) g_devs[size_t(k)]->worker->post([&job, k] { job(k); });
+    std::exception_ptr first;
+    try { job(0); } catch (...) { first = std::current_exception(); }
+    for (int k = 1; k < nLocal; ++k) {
+        try { g_devs[size_t(k)]->worker->wait(); } catch (...) { if (!first) first = std::current_exception(); }
+    }
+    if (first) std::rethrow_exception(first);
+}
+
+enum class RunKind { Value, Aad, Multi };
+
+// One run of a plan over paths [first, first + n) with host results.  With a communicator the range is sharded over
+// its participants -- the devices of this context, or this process's device among the processes of the job -- and the
+// rank sum is part of the launch; every participant ends with the full sums.
+//   hOut: outSize doubles ([n_payoffs] | [n_payoffs] agg adjoints | multi: [n_payoffs] then [nAdj][n_payoffs])
+void run_plan(cf_plan& mp, RunKind kind, const double* w, uint64_t first, uint64_t n, double* hOut, double* hPerPath,
+              double* hPerAgg)
+{
+    ensure_init();
+    g_comm.check();
+    DevPlan& p0 = mp.d0();
+    if (mp.dev.size() != g_devs.size()) throw CfError("cf_b200: this plan was created in another context");
+    const bool aad = kind != RunKind::Value;
+    const size_t nOut = kind == RunKind::Multi ? p0.multiOutSize() : p0.outSize(aad);
+    const int nPay = p0.nPay;
+    const bool shard = g_comm.on();
+    if (shard && g_comm.ipc && (hPerPath || hPerAgg))
+        throw CfError("cf_b200: per-path outputs are not gathered across the processes of a communicator");
+    if (shard && nOut > g_comm.cap) throw CfError("cf_b200: result vector longer than the communicator's capacity");
+    const int nLocal = shard ? int(mp.dev.size()) : 1;
+    const uint32_t epoch = shard ? ++g_comm.epoch : 0u;
+    double* pinned = mp.pinned(nOut);
+    auto job = [&](int k) {
+        DevPlan& p = *mp.dev[size_t(k)];
+        cudaStream_t s = p.dev->stream;                      // null in a single-device context: the legacy default stream
+        uint64_t f = 0, c = n;
+        cf::DPeers px{};
+        if (shard) { shard_range(n, g_comm.rank0 + k, g_comm.world, f, c); px = g_comm.peers(k, epoch); }
+        if (p.outBuf.n < nOut) p.outBuf.alloc(nOut, s);
+        double* dPer = nullptr;
+        double* dAgg = nullptr;
+        if (hPerPath && c) { if (p.perBuf.n < c * size_t(nPay)) p.perBuf.alloc(c * size_t(nPay), s); dPer = p.perBuf.p; }
+        if (hPerAgg && c) { if (p.aggBuf.n < c) p.aggBuf.alloc(c, s); dAgg = p.aggBuf.p; }
+        if (kind == RunKind::Multi) p.launchMulti(first + f, c, p.outBuf.p, s, shard ? &px : nullptr);
+        else p.launch(aad, w, first + f, c, p.outBuf.p, dPer, dAgg, s, shard ? &px : nullptr);
+        if (k == 0) CF_CUDA(cudaMemcpyAsync(pinned, p.outBuf.p, sizeof(double) * nOut, cudaMemcpyDeviceToHost, s));
+        if (dPer) CF_CUDA(cudaMemcpyAsync(hPerPath + f * size_t(nPay), dPer, sizeof(double) * c * size_t(nPay), cudaMemcpyDeviceToHost, s));
+        if (dAgg) CF_CUDA(cudaMemcpyAsync(hPerAgg + f, dAgg, sizeof(double) * c, cudaMemcpyDeviceToHost, s));
+        if (k == 0 || dPer || dAgg) CF_CUDA(cudaStreamSynchronize(s));
+    };
+    on_devices(nLocal, job);
+    g_comm.check();
+    std::memcpy(hOut, pinned, sizeof(double) * nOut);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
 extern "C" {
 
 const char* cf_last_error(void) { return g_err.c_str(); }
@@ -904,26 +1427,114 @@ uint64_t cf_launch_count(void) { return g_launches.load(); }
 int cf_init(int n_devices, const int* device_ids)
 {
     return guarded([&] {
-        if (n_devices != 1 || !device_ids) throw CfError("cf_init: one process drives one GPU (n_devices must be 1)");
+        if (n_devices < 1 || n_devices > cf::kMaxPeers || !device_ids) throw CfError("cf_init: 1 .. 16 devices");
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
         if (e != cudaSuccess || n == 0) throw CfError("cf_init: no CUDA device available (this library has no CPU fallback)");
-        if (device_ids[0] < 0 || device_ids[0] >= n) throw CfError("cf_init: device id out of range");
-        CF_CUDA(cudaSetDevice(device_ids[0]));
-        g_device = device_ids[0];
-        CF_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, g_device));
-        keep_pool_memory(g_device);
+        for (int k = 0; k < n_devices; ++k) {
+            if (device_ids[k] < 0 || device_ids[k] >= n) throw CfError("cf_init: device id out of range");
+            for (int j = 0; j < k; ++j) if (device_ids[j] == device_ids[k]) throw CfError("cf_init: a device is listed twice");
+        }
+        if (g_comm.world) comm_destroy();
+        close_devices();
+        for (int k = 0; k < n_devices; ++k) g_devs.push_back(open_device(device_ids[k], k, n_devices > 1));
+        t_dev = nullptr; t_gen = g_gen;
+        bind(g_devs[0].get());
         g_launches = 0;
+        if (n_devices > 1) {
+            // the devices of this process are the participants of the rank sum: peer access, receive blocks, flags
+            for (int k = 0; k < n_devices; ++k) {
+                DeviceScope sc(g_devs[size_t(k)].get());
+                for (int j = 0; j < n_devices; ++j) {
+                    if (j == k) continue;
+                    int can = 0;
+                    CF_CUDA(cudaDeviceCanAccessPeer(&can, device_ids[k], device_ids[j]));
+                    if (!can) throw CfError("cf_init: the devices of a context must have peer access to each other (NVLink)");
+                    const cudaError_t pe = cudaDeviceEnablePeerAccess(device_ids[j], 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CF_CUDA(pe);
+                    cudaGetLastError();
+                }
+            }
+            static const size_t cap = [] { const char* v = std::getenv("CF_COMM_CAPACITY"); return v ? size_t(std::atoll(v)) : (size_t(1) << 20); }();
+            comm_allocate(n_devices, 0, cap);
+            for (int k = 0; k < n_devices; ++k) g_comm.block[k] = g_comm.local[size_t(k)];
+            g_comm.enabled = true;
+        }
     });
 }
 
 int cf_shutdown(void)
 {
     return guarded([&] {
-        if (g_device >= 0) {
-            CF_CUDA(cudaDeviceSynchronize());
+        if (g_comm.world) comm_destroy();
+        close_devices();
+    });
+}
+
+int cf_device_count(void) { return int(g_devs.size()); }
+int cf_context_generation(void) { return g_gen; }
+
+/* ---- communicator over the processes of a job (one device per process) ---- */
+int cf_comm_create(int world, int rank, size_t capacity_doubles, void* handle_out)
+{
+    return guarded([&] {
+        ensure_init();
+        if (!handle_out) throw CfError("cf_comm_create: null handle");
+        if (g_devs.size() != 1) throw CfError("cf_comm_create: a process of a multi-process job drives one device");
+        if (rank < 0 || rank >= world) throw CfError("cf_comm_create: bad rank");
+        comm_allocate(world, rank, capacity_doubles);
+        g_comm.ipc = true;
+        cudaIpcMemHandle_t h;
+        CF_CUDA(cudaIpcGetMemHandle(&h, g_comm.local[0]));
+        static_assert(sizeof(cudaIpcMemHandle_t) == CF_COMM_HANDLE_BYTES, "handle size");
+        std::memcpy(handle_out, &h, sizeof(h));
+    });
+}
+
+int cf_comm_connect(const void* handles)
+{
+    return guarded([&] {
+        ensure_init();
+        if (!g_comm.world || !g_comm.ipc || !handles) throw CfError("cf_comm_connect: call cf_comm_create first");
+        for (int r = 0; r < g_comm.world; ++r) {
+            if (r == g_comm.rank0) { g_comm.block[r] = g_comm.local[0]; continue; }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const unsigned char*>(handles) + size_t(r) * CF_COMM_HANDLE_BYTES, sizeof(h));
+            void* q = nullptr;
+            CF_CUDA(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+            g_comm.opened.push_back(q);
+            g_comm.block[r] = static_cast<unsigned char*>(q);
         }
-        g_device = -1;
+        g_comm.enabled = true;
+    });
+}
+
+int cf_comm_enable(int on)
+{
+    return guarded([&] {
+        if (on && g_comm.world < 2) throw CfError("cf_comm_enable: no communicator");
+        if (on) for (int r = 0; r < g_comm.world; ++r) if (!g_comm.block[r]) throw CfError("cf_comm_enable: the communicator is not connected");
+        g_comm.enabled = on != 0;
+    });
+}
+
+int cf_comm_destroy(void) { return guarded([&] { comm_destroy(); }); }
+
+int cf_comm_info(int* world, int* rank, int* enabled)
+{
+    if (world) *world = g_comm.world;
+    if (rank) *rank = g_comm.rank0;
+    if (enabled) *enabled = g_comm.on() ? 1 : 0;
+    return 0;
+}
+
+int cf_comm_status(void) { return g_comm.status ? *reinterpret_cast<volatile int*>(g_comm.status) : 0; }
+
+int cf_shard_range(uint64_t n_paths, int rank, int world, uint64_t* first, uint64_t* count)
+{
+    return guarded([&] {
+        if (world < 1 || rank < 0 || rank >= world || !first || !count) throw CfError("cf_shard_range: bad arguments");
+        shard_range(n_paths, rank, world, *first, *count);
     });
 }
 
@@ -937,25 +1548,33 @@ int cf_plan_create(const cf_model* mdl, const cf_product* prd, const cf_rng* rng
 {
     return guarded([&] {
         if (!out) throw CfError("cf_plan_create: null out");
-        *out = make_plan(mdl, prd, rng).release();
+        *out = make_multi_plan(mdl, prd, rng).release();
     });
 }
 
-void cf_plan_destroy(cf_plan* plan)
-{
-    if (!plan) return;
-    cudaDeviceSynchronize();      // launches may be in flight on the caller's streams; the tables go back to the pool
-    delete plan;
-}
+void cf_plan_destroy(cf_plan* plan) { delete plan; }
 
-size_t cf_plan_out_size(const cf_plan* plan, int aad) { return plan ? plan->outSize(aad != 0) : 0; }
+size_t cf_plan_out_size(const cf_plan* plan, int aad) { return plan ? plan->d0().outSize(aad != 0) : 0; }
+
+namespace {
+// the participants of the rank sum for a launch on the caller's stream (one local device per process)
+const cf::DPeers* launch_peers(cf::DPeers& px)
+{
+    if (!g_comm.on()) return nullptr;
+    if (g_devs.size() != 1) throw CfError("cf_plan_launch: a multi-device context runs through cf_plan_run_* / cf_run_*");
+    g_comm.check();
+    px = g_comm.peers(0, ++g_comm.epoch);
+    return &px;
+}
+}  // namespace
 
 int cf_plan_launch_value(cf_plan* plan, uint64_t first_path, uint64_t n_paths, double* d_out, void* stream)
 {
     return guarded([&] {
         if (!plan || !d_out) throw CfError("cf_plan_launch_value: null argument");
         ensure_init();
-        plan->launch(false, nullptr, first_path, n_paths, d_out, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+        cf::DPeers px{};
+        plan->d0().launch(false, nullptr, first_path, n_paths, d_out, nullptr, nullptr, static_cast<cudaStream_t>(stream), launch_peers(px));
     });
 }
 
@@ -965,25 +1584,42 @@ int cf_plan_launch_aad(cf_plan* plan, const double* payoff_weights, uint64_t fir
     return guarded([&] {
         if (!plan || !d_out || !payoff_weights) throw CfError("cf_plan_launch_aad: null argument");
         ensure_init();
-        plan->launch(true, payoff_weights, first_path, n_paths, d_out, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+        cf::DPeers px{};
+        plan->d0().launch(true, payoff_weights, first_path, n_paths, d_out, nullptr, nullptr, static_cast<cudaStream_t>(stream), launch_peers(px));
     });
 }
 
-int cf_plan_set_peers(cf_plan* plan, int world, int rank, void* const* peer_bufs, void* const* peer_flags)
+int cf_plan_run_value(cf_plan* plan, uint64_t first_path, uint64_t n_paths, double* payoff_sums, double* per_path_payoffs)
 {
     return guarded([&] {
-        if (!plan) throw CfError("cf_plan_set_peers: null plan");
-        if (world <= 1) { plan->peers = cf::DPeers{}; return; }
-        if (world > cf::kMaxPeers || rank < 0 || rank >= world || !peer_bufs || !peer_flags) throw CfError("cf_plan_set_peers: bad arguments");
-        if (!(plan->fast && plan->hasTimeMap)) throw CfError("cf_plan_set_peers: the fused reduction is part of the Dupire fast path only");
-        cf::DPeers p{};
-        p.world = world; p.rank = rank;
-        for (int r = 0; r < world; ++r) {
-            if (!peer_bufs[r] || !peer_flags[r]) throw CfError("cf_plan_set_peers: null peer pointer");
-            p.buf[r] = static_cast<double*>(peer_bufs[r]); p.flag[r] = static_cast<uint32_t*>(peer_flags[r]);
-        }
-        plan->peers = p;
-        plan->peerEpoch = 0;
+        if (!plan || !payoff_sums) throw CfError("cf_plan_run_value: null argument");
+        std::vector<double> h(plan->d0().outSize(false));
+        run_plan(*plan, RunKind::Value, nullptr, first_path, n_paths, h.data(), per_path_payoffs, nullptr);
+        std::memcpy(payoff_sums, h.data(), sizeof(double) * size_t(plan->d0().nPay));
+    });
+}
+
+int cf_plan_run_aad(cf_plan* plan, const double* payoff_weights, uint64_t first_path, uint64_t n_paths,
+                    double* payoff_sums, double* agg_sum, double* table_adjoints, double* per_path_payoffs, double* per_path_agg)
+{
+    return guarded([&] {
+        if (!plan || !payoff_weights || !payoff_sums || !agg_sum || !table_adjoints) throw CfError("cf_plan_run_aad: null argument");
+        const DevPlan& p = plan->d0();
+        std::vector<double> h(p.outSize(true));
+        run_plan(*plan, RunKind::Aad, payoff_weights, first_path, n_paths, h.data(), per_path_payoffs, per_path_agg);
+        std::memcpy(payoff_sums, h.data(), sizeof(double) * size_t(p.nPay));
+        *agg_sum = h[size_t(p.nPay)];
+        std::memcpy(table_adjoints, h.data() + p.nPay + 1, sizeof(double) * p.nAdj);
+    });
+}
+
+int cf_plan_debug_times(cf_plan* plan, unsigned long long* out /* [3][1024][8] */)
+{
+    return guarded([&] {
+        if (!plan || !out || !plan->d0().dbgTimes.p) throw CfError("cf_plan_debug_times: run with CF_DEBUG_TIMES=1 first");
+        ensure_init();
+        CF_CUDA(cudaDeviceSynchronize());
+        CF_CUDA(cudaMemcpy(out, plan->d0().dbgTimes.p, 3 * 1024 * 8 * 8, cudaMemcpyDeviceToHost));
     });
 }
 
@@ -991,16 +1627,18 @@ int cf_plan_kernel_ms(cf_plan* plan, double* avg_ms, int* n_launches)
 {
     return guarded([&] {
         if (!plan) throw CfError("cf_plan_kernel_ms: null plan");
+        ensure_init();
+        DevPlan& p = plan->d0();
         double tot = 0.0;
         int n = 0;
-        for (auto& ev : plan->events) {
+        for (auto& ev : p.events) {
             CF_CUDA(cudaEventSynchronize(ev.second));
             float ms = 0.f;
             CF_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
             tot += ms; ++n;
-            plan->pool.push_back(ev);
+            p.pool.push_back(ev);
         }
-        plan->events.clear();
+        p.events.clear();
         if (avg_ms) *avg_ms = n ? tot / n : 0.0;
         if (n_launches) *n_launches = n;
     });
@@ -1011,15 +1649,10 @@ int cf_run_value(const cf_model* mdl, const cf_product* prd, const cf_rng* rng, 
 {
     return guarded([&] {
         if (!payoff_sums) throw CfError("cf_run_value: payoff_sums is null");
-        auto plan = make_plan(mdl, prd, rng);
-        DevBuf<double> dOut, dPer;
-        dOut.alloc(plan->outSize(false));
-        if (per_path_payoffs) dPer.alloc(n_paths * plan->nPay);
-        plan->launch(false, nullptr, first_path, n_paths, dOut.p, dPer.p, nullptr, nullptr);
-        CF_CUDA(cudaMemcpy(payoff_sums, dOut.p, sizeof(double) * plan->nPay, cudaMemcpyDeviceToHost));
-        if (per_path_payoffs)
-            CF_CUDA(cudaMemcpy(per_path_payoffs, dPer.p, sizeof(double) * n_paths * plan->nPay, cudaMemcpyDeviceToHost));
-        CF_CUDA(cudaDeviceSynchronize());
+        auto plan = make_multi_plan(mdl, prd, rng);
+        std::vector<double> h(plan->d0().outSize(false));
+        run_plan(*plan, RunKind::Value, nullptr, first_path, n_paths, h.data(), per_path_payoffs, nullptr);
+        std::memcpy(payoff_sums, h.data(), sizeof(double) * size_t(plan->d0().nPay));
     });
 }
 
@@ -1033,25 +1666,15 @@ int cf_run_aad(const cf_model* mdl, const cf_product* prd, const cf_rng* rng, ui
         auto now = [] { return std::chrono::steady_clock::now(); };
         auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
         const auto t0 = now();
-        auto plan = make_plan(mdl, prd, rng);
+        auto plan = make_multi_plan(mdl, prd, rng);
         const auto t1 = now();
-        DevBuf<double> dOut, dPer, dAgg;
-        const size_t nOut = plan->outSize(true);
-        dOut.alloc(nOut);
-        if (per_path_payoffs) dPer.alloc(n_paths * plan->nPay);
-        if (per_path_agg) dAgg.alloc(n_paths);
-        plan->launch(true, payoff_weights, first_path, n_paths, dOut.p, dPer.p, dAgg.p, nullptr);
-        const auto t2 = now();
-        std::vector<double> h(nOut);
-        CF_CUDA(cudaMemcpy(h.data(), dOut.p, sizeof(double) * nOut, cudaMemcpyDeviceToHost));
-        if (timing) std::fprintf(stderr, "cf_run_aad: make_plan %.0f us, launch calls %.0f us, wait + copy back %.0f us\n", us(t0, t1), us(t1, t2), us(t2, now()));
-        std::memcpy(payoff_sums, h.data(), sizeof(double) * plan->nPay);
-        *agg_sum = h[plan->nPay];
-        std::memcpy(table_adjoints, h.data() + plan->nPay + 1, sizeof(double) * plan->nAdj);
-        if (per_path_payoffs)
-            CF_CUDA(cudaMemcpy(per_path_payoffs, dPer.p, sizeof(double) * n_paths * plan->nPay, cudaMemcpyDeviceToHost));
-        if (per_path_agg) CF_CUDA(cudaMemcpy(per_path_agg, dAgg.p, sizeof(double) * n_paths, cudaMemcpyDeviceToHost));
-        CF_CUDA(cudaDeviceSynchronize());
+        const DevPlan& p = plan->d0();
+        std::vector<double> h(p.outSize(true));
+        run_plan(*plan, RunKind::Aad, payoff_weights, first_path, n_paths, h.data(), per_path_payoffs, per_path_agg);
+        if (timing) std::fprintf(stderr, "cf_run_aad: make_plan %.0f us, launches + wait + copy back %.0f us\n", us(t0, t1), us(t1, now()));
+        std::memcpy(payoff_sums, h.data(), sizeof(double) * size_t(p.nPay));
+        *agg_sum = h[size_t(p.nPay)];
+        std::memcpy(table_adjoints, h.data() + p.nPay + 1, sizeof(double) * p.nAdj);
     });
 }
 
@@ -1059,99 +1682,36 @@ int cf_run_aad_multi(const cf_model* mdl, const cf_product* prd, const cf_rng* r
                      uint64_t n_paths, double* payoff_sums, double* risk_tables)
 {
     return guarded([&] {
-        if (!payoff_sums || !risk_tables) throw CfError("cf_run_aad_multi: null output");
-        auto plan = make_plan(mdl, prd, rng);
-        const int nPay = plan->nPay;
-        const size_t nAdj = plan->nAdj;
+        auto plan = make_multi_plan(mdl, prd, rng);
+        if (cf_plan_run_aad_multi(plan.get(), first_path, n_paths, payoff_sums, risk_tables) != 0) throw CfError(g_err);
+    });
+}
+
+int cf_plan_run_aad_multi(cf_plan* plan, uint64_t first_path, uint64_t n_paths, double* payoff_sums, double* risk_tables)
+{
+    return guarded([&] {
+        if (!plan || !payoff_sums || !risk_tables) throw CfError("cf_run_aad_multi: null argument");
+        const DevPlan& p = plan->d0();
+        const int nPay = p.nPay;
+        const size_t nAdj = p.nAdj;
         if (n_paths == 0) throw CfError("cf_b200: n_paths must be > 0");
-        const bool special = mdl->kind == CF_MODEL_DUPIRE && prd->kind == CF_PRODUCT_EUROPEANS && plan->hasTimeMap
-                             && plan->D <= cf::kMultiMaxSteps;
-        if (!special) {
-            // one adjoint sweep per payoff: column k of the risk matrix is the aggregate risk with weights e_k
-            if (nPay > 64) throw CfError("cf_run_aad_multi: this model / product pair has too many payoffs for itemised risk on the device");
-            DevBuf<double> dOut;
-            const size_t nOut = plan->outSize(true);
-            dOut.alloc(nOut);
-            std::vector<double> h(nOut), w(size_t(nPay), 0.0);
-            for (int k = 0; k < nPay; ++k) {
-                std::fill(w.begin(), w.end(), 0.0);
-                w[size_t(k)] = 1.0;
-                plan->launch(true, w.data(), first_path, n_paths, dOut.p, nullptr, nullptr, nullptr);
-                CF_CUDA(cudaMemcpy(h.data(), dOut.p, sizeof(double) * nOut, cudaMemcpyDeviceToHost));
-                if (k == 0) std::memcpy(payoff_sums, h.data(), sizeof(double) * size_t(nPay));
-                for (size_t q = 0; q < nAdj; ++q) risk_tables[q * size_t(nPay) + size_t(k)] = h[size_t(nPay) + 1 + q];
-            }
-            CF_CUDA(cudaDeviceSynchronize());
+        if (p.multiReady) {
+            // Dupire x Europeans: one sweep per maturity, accumulated by strike class (cf_multi.cuh)
+            std::vector<double> h(p.multiOutSize());
+            run_plan(*plan, RunKind::Multi, nullptr, first_path, n_paths, h.data(), nullptr, nullptr);
+            std::memcpy(payoff_sums, h.data(), sizeof(double) * size_t(nPay));
+            std::memcpy(risk_tables, h.data() + nPay, sizeof(double) * nAdj * size_t(nPay));
             return;
         }
-        // ---- Dupire x Europeans: one sweep per maturity, accumulated by strike class (cf_multi.cuh)
-        const int D = plan->D, m = plan->m, E = plan->E, nTimes = plan->nTimes;
-        if (plan->rngKind == CF_RNG_SOBOL && first_path + n_paths > 0xffffffffull) throw CfError("cf_b200: Sobol index exceeds 2^32 - 1");
-        std::vector<double> ksorted(static_cast<size_t>(nPay));
-        std::vector<int32_t> payEvent(static_cast<size_t>(nPay)), payRank(static_cast<size_t>(nPay)), payOrig(static_cast<size_t>(nPay));
-        int cmax = 1;
-        for (int e = 0; e < E; ++e) {
-            const int k0 = prd->strike_offsets[e], k1 = prd->strike_offsets[e + 1];
-            std::vector<int> order;
-            for (int k = k0; k < k1; ++k) order.push_back(k);
-            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return prd->strikes[x] < prd->strikes[y]; });
-            for (int r = 0; r < k1 - k0; ++r) {
-                ksorted[size_t(k0 + r)] = prd->strikes[order[size_t(r)]];
-                payEvent[size_t(k0 + r)] = e; payRank[size_t(k0 + r)] = r; payOrig[size_t(k0 + r)] = order[size_t(r)];
-            }
-            cmax = std::max(cmax, k1 - k0 + 1);
+        // any other pair: one adjoint sweep per payoff, column k of the risk matrix is the aggregate risk with weights e_k
+        std::vector<double> h(p.outSize(true)), w(size_t(nPay), 0.0);
+        for (int k = 0; k < nPay; ++k) {
+            std::fill(w.begin(), w.end(), 0.0);
+            w[size_t(k)] = 1.0;
+            run_plan(*plan, RunKind::Aad, w.data(), first_path, n_paths, h.data(), nullptr, nullptr);
+            if (k == 0) std::memcpy(payoff_sums, h.data(), sizeof(double) * size_t(nPay));
+            for (size_t q = 0; q < nAdj; ++q) risk_tables[q * size_t(nPay) + size_t(k)] = h[size_t(nPay) + 1 + q];
         }
-        // class of a path = #strikes strictly below S_e; a payoff is in the money for classes above the position of
-        // the LAST strike equal to its own
-        for (int e = 0; e < E; ++e) {
-            const int k0 = prd->strike_offsets[e], k1 = prd->strike_offsets[e + 1];
-            for (int r = 0; r < k1 - k0; ++r) {
-                int last = r;
-                while (last + 1 < k1 - k0 && ksorted[size_t(k0 + last + 1)] == ksorted[size_t(k0 + r)]) ++last;
-                payRank[size_t(k0 + r)] = last;
-            }
-        }
-        const size_t tabLen = 1 + size_t(D) * m;
-        DevBuf<double> dK, dT, dPartial, dSums, dOut;
-        DevBuf<int32_t> dEv, dRank, dOrig;
-        dK.upload(ksorted.data(), ksorted.size());
-        dEv.upload(payEvent.data(), payEvent.size()); dRank.upload(payRank.data(), payRank.size()); dOrig.upload(payOrig.data(), payOrig.size());
-        dT.alloc(size_t(E) * cmax * tabLen);
-        CF_CUDA(cudaMemset(dT.p, 0, sizeof(double) * dT.n));
-        const uint64_t nb64 = (n_paths + cf::kBlock - 1) / cf::kBlock;
-        if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
-        const int grid = int(std::min<uint64_t>(nb64, uint64_t(2) * g_sms));
-        dPartial.alloc(size_t(grid) * nPay);
-        dSums.alloc(size_t(nPay));
-        cf::MArgs a{};
-        a.first_path = first_path; a.n_paths = n_paths; a.n_batches = int(nb64);
-        a.seed1 = rng->seed1; a.seed2 = rng->seed2; a.dim = plan->dim;
-        a.sobol_dir = plan->sobolDir.p; a.mrg_jump = plan->mrgJump.p;
-        a.D = D; a.m = m; a.E = E; a.is_event = plan->isEvent.p; a.spot = mdl->spot;
-        a.interp_vols = plan->tabA.p; a.log_spots = plan->tabB.p;
-        a.ksorted = dK.p; a.koff = plan->eOff.p; a.n_payoffs = nPay; a.cmax = cmax;
-        a.partial = dPartial.p; a.T = dT.p; a.per_path_payoffs = nullptr;
-        const bool sob = plan->rngKind == CF_RNG_SOBOL;
-        const size_t smem = cf::multi_smem(D, m, nPay, plan->dim, sob).total;
-        if (smem > kFastSmemLimit / 2) throw CfError("cf_run_aad_multi: tables do not fit in shared memory");
-        auto fn = cf::pick_multi_kernel(plan->rngKind);
-        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        fn<<<grid, cf::kBlock, smem>>>(a);
-        CF_CUDA(cudaGetLastError());
-        cf::reduce_partials_kernel<<<(nPay + 127) / 128, 128>>>(dPartial.p, grid, nPay, nPay, dSums.p);
-        const size_t nSuffix = size_t(E) * tabLen;
-        cf::multi_suffix_kernel<<<unsigned((nSuffix + 255) / 256), 256>>>(dT.p, E, cmax, tabLen);
-        const size_t nParam = 1 + size_t(m) * nTimes;
-        dOut.alloc(nParam * nPay);
-        cf::multi_collapse_kernel<<<unsigned((nParam * nPay + 255) / 256), 256>>>(dT.p, E, cmax, D, m, nTimes, plan->tk1.p, plan->tk2.p,
-                                                                                 plan->tc1.p, plan->tc2.p, dEv.p, dRank.p, dOrig.p, nPay, dOut.p);
-        CF_CUDA(cudaGetLastError());
-        g_launches += 4;
-        std::vector<double> sums(static_cast<size_t>(nPay));
-        CF_CUDA(cudaMemcpy(sums.data(), dSums.p, sizeof(double) * size_t(nPay), cudaMemcpyDeviceToHost));
-        for (int ps = 0; ps < nPay; ++ps) payoff_sums[payOrig[size_t(ps)]] = sums[size_t(ps)];
-        CF_CUDA(cudaMemcpy(risk_tables, dOut.p, sizeof(double) * nParam * nPay, cudaMemcpyDeviceToHost));
-        CF_CUDA(cudaDeviceSynchronize());
     });
 }
 

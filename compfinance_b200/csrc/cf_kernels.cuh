@@ -21,6 +21,7 @@
 #pragma once
 
 #include "cf_device.cuh"
+#include "cf_comm.cuh"
 #include "../../include/cf_b200.h"
 
 namespace cf {

@@ -12,9 +12,11 @@
 // c = #{k : K_k < S_e}; the risk of payoff (e, k) is the sum of the tables of classes > rank(k),
 // taken afterwards (suffix sums), together with the time interpolation of init().
 //
-// Accumulation: fp64 reductions in L2 (RED.ADD.F64) into [event][class][1 + steps x knots].  Sums of
-// 2^22 paths in arbitrary order agree to ~1e-15 relative, not bitwise (the reference's own risks move
-// by ~1e-13 with thread scheduling).
+// Accumulation: every thread adds into [event][class][1 + steps x knots] in L2.  To be bit-reproducible whatever
+// the order the adds arrive in, an addend x is split into two FIXED-POINT integers -- hi = rint(x 2^10) and
+// lo = rint((x - hi 2^-10) 2^b), b = 50 for up to 2^22 paths -- added with 64-bit integer atomics (associative:
+// same bits on every run, every grid, every GPU).  What is dropped is below 2^-(b+1) per addend (1e-15);
+// |x| N < 2^52 is required of hi (x < 1e9 for 2^22 paths) and checked by the host against the spot.
 #pragma once
 
 #include "cf_kernels.cuh"
@@ -39,7 +41,9 @@ struct MArgs {
     const int32_t* koff;           // [E + 1]
     int      n_payoffs, cmax;      // cmax = 1 + max strikes per event
     double*  partial;              // [grid][n_payoffs] payoff sums (sorted order)
-    double*  T;                    // [E][cmax][1 + D * m]: spot adjoint, then interp_vols adjoints; zeroed by the host
+    long long* Thi;                // [E][cmax][1 + D * m]: spot adjoint, then interp_vols adjoints, fixed point 2^-10; zeroed by the host
+    long long* Tlo;                // the remainders, fixed point 2^-lo_bits
+    double   lo_scale;             // 2^lo_bits
     double*  per_path_payoffs;     // [n_paths][n_payoffs] (sorted order) or null
 };
 
@@ -138,7 +142,16 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks[mid] < S) lo = mid + 1; else hi = mid; }
             const int c = lo - k0;
             if (!valid || c == 0) return;
-            double* T = a.T + (size_t(e) * a.cmax + c) * tabLen;
+            const size_t tOff = (size_t(e) * a.cmax + c) * tabLen;
+            unsigned long long* Thi = reinterpret_cast<unsigned long long*>(a.Thi) + tOff;
+            unsigned long long* Tlo = reinterpret_cast<unsigned long long*>(a.Tlo) + tOff;
+            const double loScale = a.lo_scale;
+            auto addFixed = [&](size_t q, double x) {              // order-independent: two integer atomics
+                const long long hi = __double2ll_rn(x * 1024.0);
+                const long long lo = __double2ll_rn(fma(double(hi), -1.0 / 1024.0, x) * loScale);
+                if (hi) atomicAdd(Thi + q, static_cast<unsigned long long>(hi));
+                if (lo) atomicAdd(Tlo + q, static_cast<unsigned long long>(lo));
+            };
             double Lbar = S;                                         // dS/dL
             for (int i = nst - 1; i >= 0; --i) {
                 const double Li = Lh[i];
@@ -156,12 +169,12 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
                 }
                 const double vbar = Lbar * (gh[i] - v);
                 const double bb = vbar * t;
-                double* row = T + 1 + size_t(i) * m + b.n;
-                if (vbar - bb != 0.0) atomicAdd(row, vbar - bb);
-                if (bb != 0.0) atomicAdd(row + 1, bb);
+                const size_t row = 1 + size_t(i) * m + b.n;
+                if (vbar - bb != 0.0) addFixed(row, vbar - bb);
+                if (bb != 0.0) addFixed(row + 1, bb);
                 Lbar += vbar * slope;
             }
-            atomicAdd(T, Lbar / a.spot);                             // L0 = log(S0), mcMdlDupire.h:245
+            addFixed(0, Lbar / a.spot);                              // L0 = log(S0), mcMdlDupire.h:245
         };
 
         double X = logS0;
@@ -194,17 +207,19 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
     }
 }
 
-// T[e][c] <- sum over classes c' >= c of T[e][c'] (in place), one thread per table entry
-static __global__ void multi_suffix_kernel(double* __restrict__ T, int E, int cmax, size_t tabLen)
+// T[e][c] <- sum over classes c' >= c of the fixed-point tables (integer suffix sums: exact), converted to double;
+// one thread per table entry
+static __global__ void multi_suffix_kernel(const long long* __restrict__ Thi, const long long* __restrict__ Tlo, double loInv,
+                                           double* __restrict__ T, int E, int cmax, size_t tabLen)
 {
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= size_t(E) * tabLen) return;
     const size_t e = idx / tabLen, q = idx % tabLen;
-    double run = 0.0;
+    long long hi = 0, lo = 0;
     for (int c = cmax - 1; c >= 0; --c) {
-        double* cell = T + (e * cmax + c) * tabLen + q;
-        run += *cell;
-        *cell = run;
+        const size_t cell = (e * cmax + c) * tabLen + q;
+        hi += Thi[cell]; lo += Tlo[cell];
+        T[cell] = fma(double(lo), loInv, double(hi) * (1.0 / 1024.0));
     }
 }
 
@@ -215,7 +230,7 @@ static __global__ void multi_collapse_kernel(const double* __restrict__ T, int E
                                       const int32_t* __restrict__ k1, const int32_t* __restrict__ k2,
                                       const double* __restrict__ c1, const double* __restrict__ c2,
                                       const int32_t* __restrict__ payEvent, const int32_t* __restrict__ payRank,
-                                      const int32_t* __restrict__ payOrig, int nPay, double* __restrict__ out)
+                                      const int32_t* __restrict__ payOrig, int nPay, double* __restrict__ out)   // out: [nParam][nPay]
 {
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const size_t nParam = 1 + size_t(m) * nTimes;
@@ -238,6 +253,14 @@ static __global__ void multi_collapse_kernel(const double* __restrict__ T, int E
         }
     }
     out[param * nPay + payOrig[ps]] = s;
+}
+
+// payoff sums from sorted to original order
+static __global__ void multi_unsort_kernel(const double* __restrict__ sorted, const int32_t* __restrict__ payOrig, int nPay,
+                                           double* __restrict__ out)
+{
+    const int ps = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ps < nPay) out[payOrig[ps]] = sorted[ps];
 }
 
 }  // namespace cf

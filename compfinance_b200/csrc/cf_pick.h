@@ -20,6 +20,7 @@ LKernel pick_dlm_kernel(int n_assets, int prd, bool aad, int rng);
 // chunk = steps of Gaussians per fill (kFwdChunk; kFwdChunk1 is also built for fwdP = 1)
 DKernel pick_dupire_forward(int prd, bool aad, int rng, int fwdP, int chunk);
 DKernel pick_dupire_reverse(int prd);
-DKernel pick_dupire_reverse_quad(int prd);      // four lanes per live path (small shards)
+int dupire_span_steps(int n_steps);             // steps per lane of the span reverse kernel for this timeline, 0: none
+DKernel pick_dupire_reverse_span(int prd, int S);   // one warp per live path, S steps per lane      // four lanes per live path (small shards)
 
 }  // namespace cf

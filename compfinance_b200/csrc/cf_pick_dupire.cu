@@ -25,8 +25,31 @@ DKernel pick_dupire_reverse(int prd)
     return prd == CF_PRODUCT_UOC ? dupire_reverse_kernel<CF_PRODUCT_UOC> : dupire_reverse_kernel<CF_PRODUCT_EUROPEAN>;
 }
 
-DKernel pick_dupire_reverse_quad(int prd)
+namespace {
+template <int S>
+DKernel pickS(int prd) { return prd == CF_PRODUCT_UOC ? dupire_reverse_span_kernel<CF_PRODUCT_UOC, S> : dupire_reverse_span_kernel<CF_PRODUCT_EUROPEAN, S>; }
+}  // namespace
+
+// steps per lane for which the span kernel is built: the smallest one >= ceil(n_steps / 32), 0 if there is none
+int dupire_span_steps(int n_steps)
 {
-    return prd == CF_PRODUCT_UOC ? dupire_reverse_quad_kernel<CF_PRODUCT_UOC> : dupire_reverse_quad_kernel<CF_PRODUCT_EUROPEAN>;
+    const int need = (n_steps + 31) / 32;
+    for (int s : {1, 2, 3, 4, 5, 6, 8}) if (s >= need) return s;
+    return 0;
 }
+
+DKernel pick_dupire_reverse_span(int prd, int S)
+{
+    switch (S) {
+        case 1: return pickS<1>(prd);
+        case 2: return pickS<2>(prd);
+        case 3: return pickS<3>(prd);
+        case 4: return pickS<4>(prd);
+        case 5: return pickS<5>(prd);
+        case 6: return pickS<6>(prd);
+        case 8: return pickS<8>(prd);
+        default: return nullptr;
+    }
+}
+
 }  // namespace cf

@@ -29,6 +29,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/cf_b200.h"
@@ -221,20 +222,132 @@ inline void cfBuildImages(const Product<T>& prd, Model<T>& initialisedMdl, const
         throw std::runtime_error("This RNG has no device image: it cannot run on the CUDA engine");
 }
 
-// Sums only (what main.h actually consumes): payoff sums over paths.
-inline std::vector<double> cfSimulSums(const Product<double>& prd, const Model<double>& mdl, const RNG& rng,
-                                       const size_t nPath, std::vector<double>* perPath = nullptr)
+// ---------------------------------------------------------------------------------------------
+// Resident sessions.  The reference's entry points look their model and product up in the store by name and run
+// on a pool of threads that lives as long as the process (xlExport.cpp:1605); a risk report is asked for again and
+// again on the same stored objects.  What does not depend on the call -- the clone of the model initialised on the
+// product's timeline (for AAD: on its own tape, parameters and init() before the mark, mcBase.h:537-561), the flat
+// device images and the engine's plan with its tables resident in HBM -- is therefore kept per (model, product, RNG)
+// and reused until one of them is put again (cf_store.h serial numbers), the evaluation date moves or the device
+// context changes.  CF_HOST_CACHE=0 in the environment switches the reuse off (every call rebuilds everything).
+// ---------------------------------------------------------------------------------------------
+struct CfSessionKey
+{
+    uint64_t modelSerial = 0, productSerial = 0;     // 0: not from the store, never cached
+    int      rngKind = 0;
+    uint32_t seed1 = 0, seed2 = 0;
+    double   sysTime = 0.0;
+    int      contextGen = 0;
+    bool     aad = false;
+    bool operator==(const CfSessionKey& o) const
+    {
+        return modelSerial == o.modelSerial && productSerial == o.productSerial && rngKind == o.rngKind && seed1 == o.seed1
+               && seed2 == o.seed2 && sysTime == o.sysTime && contextGen == o.contextGen && aad == o.aad;
+    }
+};
+
+struct CfSession
+{
+    CfSessionKey                   key;
+    std::unique_ptr<Model<Number>> mdlN;      // AAD: initialised clone, recorded on `tape`
+    std::unique_ptr<Model<double>> mdlD;      // value
+    Tape                           tape;
+    CfDeviceSetup                  setup;     // PODs point into its own vectors: a session is never moved
+    cf_plan*                       plan = nullptr;
+    size_t                         nAdj = 0, nPay = 0;
+    CfSession() = default;
+    CfSession(const CfSession&) = delete;
+    CfSession& operator=(const CfSession&) = delete;
+    ~CfSession() { if (plan) cf_plan_destroy(plan); }
+};
+
+// Number::tape points at the session's tape while the session is worked on
+struct CfTapeScope
+{
+    Tape* saved;
+    explicit CfTapeScope(Tape* t) : saved(Number::tape) { Number::tape = t; }
+    ~CfTapeScope() { Number::tape = saved; }
+};
+
+inline bool cfHostCacheEnabled()
+{
+    static const bool on = [] { const char* e = std::getenv("CF_HOST_CACHE"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
+
+inline std::vector<std::unique_ptr<CfSession>>& cfSessions() { static std::vector<std::unique_ptr<CfSession>> v; return v; }
+
+inline CfSessionKey cfMakeKey(const uint64_t modelSerial, const uint64_t productSerial, const RNG& rng, const bool aad)
+{
+    CfSessionKey k;
+    cf_rng r{};
+    if (!rng.deviceImage(r)) throw std::runtime_error("This RNG has no device image: it cannot run on the CUDA engine");
+    k.modelSerial = modelSerial; k.productSerial = productSerial; k.rngKind = r.kind; k.seed1 = r.seed1; k.seed2 = r.seed2;
+    k.sysTime = systemTime; k.contextGen = cf_context_generation(); k.aad = aad;
+    return k;
+}
+
+// Builds the session: clone, allocate, init (AAD: on the session's tape, then mark), device images, resident plan.
+template <class T>
+inline std::unique_ptr<CfSession> cfBuildSession(const Product<T>& prd, const Model<T>& mdl, const RNG& rng, const bool aad)
 {
     if (!checkCompatiblity(prd, mdl)) throw std::runtime_error("Model and product are not compatible");
+    auto s = std::make_unique<CfSession>();
+    CfTapeScope scope(&s->tape);
     auto cMdl = mdl.clone();
     cMdl->allocate(prd.timeline(), prd.defline());
-    cMdl->init(prd.timeline(), prd.defline());
-    CfDeviceSetup s;
-    cfBuildImages(prd, *cMdl, rng, s);
-    const size_t nPay = prd.payoffLabels().size();
-    std::vector<double> sums(nPay);
-    if (perPath) perPath->resize(nPath * nPay);
-    cfCheck(cf_run_value(&s.mdl.pod, &s.prd.pod, &s.rng, 0, nPath, sums.data(), perPath ? perPath->data() : nullptr));
+    if constexpr (std::is_same<T, Number>::value) {
+        // AAD - 1 (mcBase.h:455-472): parameters and init() on tape, then mark
+        s->tape.clear();
+        cMdl->putParametersOnTape();
+        cMdl->init(prd.timeline(), prd.defline());
+        s->tape.mark();
+    } else {
+        cMdl->init(prd.timeline(), prd.defline());
+    }
+    cfBuildImages(prd, *cMdl, rng, s->setup);
+    s->nPay = prd.payoffLabels().size();
+    s->nAdj = cf_table_adjoint_size(&s->setup.mdl.pod, &s->setup.prd.pod);
+    if (aad && s->nAdj != s->setup.mdl.adjointTargets.size())
+        throw std::runtime_error("mcSimulAAD: device adjoint layout does not match the model's host tables");
+    cfCheck(cf_plan_create(&s->setup.mdl.pod, &s->setup.prd.pod, &s->setup.rng, &s->plan));
+    if constexpr (std::is_same<T, Number>::value) s->mdlN = std::move(cMdl); else s->mdlD = std::move(cMdl);
+    return s;
+}
+
+// The session of `key` if it is resident, else a new one (kept when the key is cacheable; at most 16 are kept).
+template <class T>
+inline CfSession* cfAcquireSession(const Product<T>& prd, const Model<T>& mdl, const RNG& rng, const CfSessionKey* key,
+                                   const bool aad, std::unique_ptr<CfSession>& owner)
+{
+    const bool cacheable = key && key->modelSerial && key->productSerial && cfHostCacheEnabled();
+    auto& all = cfSessions();
+    if (cacheable)
+        for (auto& s : all) if (s->key == *key) return s.get();
+    auto fresh = cfBuildSession(prd, mdl, rng, aad);
+    if (!cacheable) { owner = std::move(fresh); return owner.get(); }
+    fresh->key = *key;
+    // sessions of objects that have been put again or of a closed context can never be hit: drop them
+    all.erase(std::remove_if(all.begin(), all.end(), [&](const std::unique_ptr<CfSession>& s) {
+                  return s->key.contextGen != key->contextGen;
+              }), all.end());
+    if (all.size() >= 16) all.erase(all.begin());
+    all.push_back(std::move(fresh));
+    return all.back().get();
+}
+
+inline void cfDropSessions() { cfSessions().clear(); }
+
+// Sums only (what main.h actually consumes): payoff sums over paths.
+inline std::vector<double> cfSimulSums(const Product<double>& prd, const Model<double>& mdl, const RNG& rng,
+                                       const size_t nPath, std::vector<double>* perPath = nullptr,
+                                       const CfSessionKey* key = nullptr)
+{
+    std::unique_ptr<CfSession> owner;
+    CfSession* s = cfAcquireSession(prd, mdl, rng, key, false, owner);
+    std::vector<double> sums(s->nPay);
+    if (perPath) perPath->resize(nPath * s->nPay);
+    cfCheck(cf_plan_run_value(s->plan, 0, nPath, sums.data(), perPath ? perPath->data() : nullptr));
     return sums;
 }
 
@@ -307,54 +420,39 @@ inline std::vector<double> cfAggregatorWeights(const F& aggFun, const size_t nPa
 // paths + adjoint sweep on the device, mark-to-start propagation on the host.
 inline AADSums cfSimulAADSums(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng, const size_t nPath,
                               const std::vector<double>& weights, std::vector<double>* perPathPayoffs = nullptr,
-                              std::vector<double>* perPathAgg = nullptr)
+                              std::vector<double>* perPathAgg = nullptr, const CfSessionKey* key = nullptr)
 {
-    if (!checkCompatiblity(prd, mdl)) throw std::runtime_error("Model and product are not compatible");
     static const bool timing = std::getenv("CF_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
     const auto t0 = now();
-    auto cMdl = mdl.clone();
-    cMdl->allocate(prd.timeline(), prd.defline());
-
-    const size_t nPay = prd.payoffLabels().size();
-    const std::vector<Number*>& params = cMdl->parameters();
-    const size_t nParam = params.size();
-
-    // AAD - 1 (mcBase.h:455-472): parameters and init() on tape, then mark
-    Tape& tape = *Number::tape;
-    tape.clear();
-    cMdl->putParametersOnTape();
-    cMdl->init(prd.timeline(), prd.defline());
-    tape.mark();
-
+    std::unique_ptr<CfSession> owner;
+    CfSession* s = cfAcquireSession(prd, mdl, rng, key, true, owner);
+    CfTapeScope scope(&s->tape);
+    const std::vector<Number*>& params = s->mdlN->parameters();
+    const size_t nParam = params.size(), nPay = s->nPay, nAdj = s->nAdj;
+    if (weights.size() != nPay) throw std::runtime_error("mcSimulAAD: one weight per payoff");
     const auto t1 = now();
-    CfDeviceSetup s;
-    cfBuildImages(prd, *cMdl, rng, s);
-    const size_t nAdj = cf_table_adjoint_size(&s.mdl.pod, &s.prd.pod);
-    if (nAdj != s.mdl.adjointTargets.size())
-        throw std::runtime_error("mcSimulAAD: device adjoint layout does not match the model's host tables");
-    const auto t2 = now();
 
     AADSums out;
     out.payoffSums.resize(nPay);
     std::vector<double> adj(nAdj);
     if (perPathPayoffs) perPathPayoffs->resize(nPath * nPay);
     if (perPathAgg) perPathAgg->resize(nPath);
-    cfCheck(cf_run_aad(&s.mdl.pod, &s.prd.pod, &s.rng, 0, nPath, weights.data(), out.payoffSums.data(), &out.aggSum,
-                       adj.data(), perPathPayoffs ? perPathPayoffs->data() : nullptr,
-                       perPathAgg ? perPathAgg->data() : nullptr));
+    cfCheck(cf_plan_run_aad(s->plan, weights.data(), 0, nPath, out.payoffSums.data(), &out.aggSum, adj.data(),
+                            perPathPayoffs ? perPathPayoffs->data() : nullptr, perPathAgg ? perPathAgg->data() : nullptr));
 
-    const auto t3 = now();
+    const auto t2 = now();
     // AAD - 4 (mcBase.h:512-527): adjoints accumulated over paths on the pre-mark nodes, one sweep mark -> start
+    s->tape.resetAdjoints();
+    const auto& targets = s->setup.mdl.adjointTargets;
     for (size_t k = 0; k < nAdj; ++k)
-        if (s.mdl.adjointTargets[k]) s.mdl.adjointTargets[k]->adjoint() += adj[k];
+        if (targets[k]) targets[k]->adjoint() += adj[k];
     Number::propagateMarkToStart();
     out.risks.resize(nParam);
     for (size_t j = 0; j < nParam; ++j) out.risks[j] = params[j]->adjoint() / double(nPath);
-    tape.clear();
-    if (timing) std::fprintf(stderr, "cfSimulAADSums: clone + init on tape %.0f us, device images %.0f us, cf_run_aad %.0f us, chain rule %.0f us\n",
-                             us(t0, t1), us(t1, t2), us(t2, t3), us(t3, now()));
+    if (timing) std::fprintf(stderr, "cfSimulAADSums: session (clone + init on tape + images + plan, or reuse) %.0f us, device run %.0f us, chain rule %.0f us\n",
+                             us(t0, t1), us(t1, t2), us(t2, now()));
     return out;
 }
 
@@ -398,51 +496,50 @@ struct AADMultiSums
 // Core of mcSimulAADMulti / mcParallelSimulAADMulti (mcBase.h:776, 859): the device returns, per payoff, the
 // adjoints of the init() tables summed over paths; the host sweeps its tape mark -> start once per payoff
 // (the reference does the same sweep with nPay adjoints per node, AADNode.h:85-102).
-inline AADMultiSums cfSimulAADMultiSums(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng, const size_t nPath)
+inline AADMultiSums cfSimulAADMultiSums(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng, const size_t nPath,
+                                        std::vector<double>* perPathPayoffs = nullptr, const CfSessionKey* key = nullptr)
 {
-    if (!checkCompatiblity(prd, mdl)) throw std::runtime_error("Model and product are not compatible");
-    auto cMdl = mdl.clone();
-    cMdl->allocate(prd.timeline(), prd.defline());
-    const size_t nPay = prd.payoffLabels().size();
-    const std::vector<Number*>& params = cMdl->parameters();
-    const size_t nParam = params.size();
-
-    Tape& tape = *Number::tape;
-    tape.clear();
-    cMdl->putParametersOnTape();
-    cMdl->init(prd.timeline(), prd.defline());
-    tape.mark();
-
-    CfDeviceSetup s;
-    cfBuildImages(prd, *cMdl, rng, s);
-    const size_t nAdj = cf_table_adjoint_size(&s.mdl.pod, &s.prd.pod);
-    if (nAdj != s.mdl.adjointTargets.size())
-        throw std::runtime_error("mcSimulAADMulti: device adjoint layout does not match the model's host tables");
+    std::unique_ptr<CfSession> owner;
+    CfSession* s = cfAcquireSession(prd, mdl, rng, key, true, owner);
+    CfTapeScope scope(&s->tape);
+    const std::vector<Number*>& params = s->mdlN->parameters();
+    const size_t nParam = params.size(), nPay = s->nPay, nAdj = s->nAdj;
 
     AADMultiSums out;
     out.payoffSums.resize(nPay);
     std::vector<double> tables(nAdj * nPay);
-    cfCheck(cf_run_aad_multi(&s.mdl.pod, &s.prd.pod, &s.rng, 0, nPath, out.payoffSums.data(), tables.data()));
+    cfCheck(cf_plan_run_aad_multi(s->plan, 0, nPath, out.payoffSums.data(), tables.data()));
+    if (perPathPayoffs) {
+        // the per-path payoffs do not depend on the AAD mode: a value run of the same plan on the same paths
+        std::vector<double> sums(nPay);
+        perPathPayoffs->resize(nPath * nPay);
+        cfCheck(cf_plan_run_value(s->plan, 0, nPath, sums.data(), perPathPayoffs->data()));
+    }
 
+    const auto& targets = s->setup.mdl.adjointTargets;
     out.risks.resize(nParam, nPay);
     for (size_t k = 0; k < nPay; ++k) {
-        tape.resetAdjoints();
+        s->tape.resetAdjoints();
         for (size_t q = 0; q < nAdj; ++q)
-            if (s.mdl.adjointTargets[q]) s.mdl.adjointTargets[q]->adjoint() += tables[q * nPay + k];
+            if (targets[q]) targets[q]->adjoint() += tables[q * nPay + k];
         Number::propagateMarkToStart();
         for (size_t j = 0; j < nParam; ++j) out.risks[j][k] = params[j]->adjoint() / double(nPath);
     }
-    tape.clear();
     return out;
 }
 
-// mcSimulAADMulti (mcBase.h:776).  The per-path payoff matrix of the reference result is filled from a value
-// run on the same paths (the payoffs do not depend on the AAD mode).
+// mcSimulAADMulti (mcBase.h:776).  The reference result carries the per-path payoff matrix (mcBase.h:758-771): it is
+// filled from a value run on the same paths as long as it stays below 2^27 doubles (1 GB; config 4 at its full 2^22
+// paths x 720 payoffs would be 24 GB on the host -- the entry points of main.h only average it), else left empty.
 inline AADMultiSimulResults mcSimulAADMulti(const Product<Number>& prd, const Model<Number>& mdl, const RNG& rng, const size_t nPath)
 {
-    AADMultiSums sums = cfSimulAADMultiSums(prd, mdl, rng, nPath);
     const size_t nPay = prd.payoffLabels().size();
-    AADMultiSimulResults results(0, nPay, sums.risks.rows());
+    const bool withPaths = double(nPath) * double(nPay) <= double(size_t(1) << 27);
+    std::vector<double> flat;
+    AADMultiSums sums = cfSimulAADMultiSums(prd, mdl, rng, nPath, withPaths ? &flat : nullptr);
+    AADMultiSimulResults results(withPaths ? nPath : 0, nPay, sums.risks.rows());
+    if (withPaths)
+        for (size_t i = 0; i < nPath; ++i) std::copy(flat.begin() + i * nPay, flat.begin() + (i + 1) * nPay, results.payoffs[i].begin());
     results.risks = std::move(sums.risks);
     return results;
 }

@@ -55,8 +55,17 @@ const char* cfx_last_error() { return g_err.c_str(); }
 
 int cfx_init(int device)
 {
-    return guarded([&] { cfCheck(cf_init(1, &device)); });
+    return guarded([&] { cfDropSessions(); cfCheck(cf_init(1, &device)); });
 }
+
+// A single-process multi-device context: every run through the entry points below is sharded over these devices.
+int cfx_init_devices(int n, const int* devices)
+{
+    return guarded([&] { cfDropSessions(); cfCheck(cf_init(n, devices)); });
+}
+
+// Drops the resident sessions (clones, tapes, device plans) the entry points keep per (model, product, RNG).
+void cfx_drop_sessions() { cfDropSessions(); }
 
 void cfx_set_system_time(double t) { systemTime = t; }
 
@@ -194,7 +203,7 @@ int cfx_simul_paths(const char* modelId, const char* productId, int useSobol, in
         const Model<double>* mdl = getModel<double>(modelId);
         const Product<double>* prd = getProduct<double>(productId);
         if (!mdl || !prd) throw std::runtime_error("model / product not found");
-        auto rng = cfMakeRng(mkNum(parallel, useSobol, numPath, seed1, seed2));
+        auto rng = cfdrv::makeRng(mkNum(parallel, useSobol, numPath, seed1, seed2));
         auto res = parallel ? mcParallelSimul(*prd, *mdl, *rng, numPath) : mcSimul(*prd, *mdl, *rng, numPath);
         const size_t nPay = prd->payoffLabels().size();
         for (size_t i = 0; i < res.size(); ++i) std::copy(res[i].begin(), res[i].end(), out + i * nPay);
@@ -224,7 +233,7 @@ int cfx_simul_aad_paths(const char* modelId, const char* productId, int riskPayo
         const Model<Number>* mdl = getModel<Number>(modelId);
         const Product<Number>* prd = getProduct<Number>(productId);
         if (!mdl || !prd) throw std::runtime_error("model / product not found");
-        auto rng = cfMakeRng(mkNum(parallel, useSobol, numPath, seed1, seed2));
+        auto rng = cfdrv::makeRng(mkNum(parallel, useSobol, numPath, seed1, seed2));
         const size_t k = riskPayoffIdx < 0 ? 0 : size_t(riskPayoffIdx);
         auto agg = [k](const std::vector<Number>& v) { return v[k]; };
         auto res = parallel ? mcParallelSimulAAD(*prd, *mdl, *rng, numPath, agg) : mcSimulAAD(*prd, *mdl, *rng, numPath, agg);
@@ -371,7 +380,7 @@ int cfx_describe(const char* modelId, const char* productId, int aad, int* dims,
 int cfx_rng_sequence(int useSobol, int seed1, int seed2, int dim, unsigned skip, int n, int gaussian, double* out)
 {
     return guarded([&] {
-        auto rng = cfMakeRng(mkNum(1, useSobol, n, seed1, seed2));
+        auto rng = cfdrv::makeRng(mkNum(1, useSobol, n, seed1, seed2));
         rng->init(size_t(dim));
         if (skip) rng->skipTo(skip);
         std::vector<double> v(static_cast<size_t>(dim));

@@ -14,18 +14,26 @@ using ProductStore = std::unordered_map<std::string, std::pair<std::unique_ptr<P
 
 inline ModelStore modelStore;
 inline ProductStore productStore;
+// Every put gives the entry a new serial number: what the entry points key their resident device plans on
+// (cf_base.h: CfSessionKey), so that overwriting a name invalidates the plans built from the old object.
+inline std::unordered_map<std::string, uint64_t> modelSerial, productSerial;
+inline uint64_t storeSerialCounter = 0;
+inline uint64_t cfModelSerial(const std::string& store) { auto it = modelSerial.find(store); return it == modelSerial.end() ? 0 : it->second; }
+inline uint64_t cfProductSerial(const std::string& store) { auto it = productSerial.find(store); return it == productSerial.end() ? 0 : it->second; }
 
 template <template <class> class M, class... Args>
 inline void cfPutModel(const std::string& store, const Args&... args)
 {
     modelStore[store] = std::make_pair(std::unique_ptr<Model<double>>(new M<double>(args...)),
                                        std::unique_ptr<Model<Number>>(new M<Number>(args...)));
+    modelSerial[store] = ++storeSerialCounter;
 }
 template <template <class> class P, class... Args>
 inline void cfPutProduct(const std::string& store, const Args&... args)
 {
     productStore[store] = std::make_pair(std::unique_ptr<Product<double>>(new P<double>(args...)),
                                          std::unique_ptr<Product<Number>>(new P<Number>(args...)));
+    productSerial[store] = ++storeSerialCounter;
 }
 
 inline void putBlackScholes(const double spot, const double vol, const bool qSpot, const double rate, const double div,

@@ -124,9 +124,20 @@ typedef struct cf_product {
 /* ------------------------------------------------------------------------------------------
  * Context
  * ---------------------------------------------------------------------------------------- */
-/* Bind this process to CUDA device device_ids[0] (one process per GPU; n_devices must be 1). */
+/* Open the context on the CUDA devices device_ids[0 .. n_devices) (1 to 16, distinct).
+ * The reference's entry points run over a process-wide pool of worker threads started once
+ * (ThreadPool::getInstance()->start, xlExport.cpp:1605); here the workers are GPUs.  With one device the calling
+ * thread drives it.  With several (they must have peer access: NVLink) every run through cf_run_* and cf_plan_run_*
+ * is sharded over them in disjoint skip-ahead blocks of paths (cf_shard_range), one host thread per device issuing
+ * the launches at the same time, and the sum over devices is part of the final reduction kernels (peer memory);
+ * results are identical on every device and read from the first.  Without cf_init the first call opens a context
+ * on the current CUDA device. */
 int cf_init(int n_devices, const int* device_ids);
 int cf_shutdown(void);
+int cf_device_count(void);   /* devices of the open context, 0 before the first call */
+/* Bumped whenever the context is closed (cf_init again, cf_shutdown): plans created before are dead (their calls fail,
+ * cf_plan_destroy stays valid); callers that cache plans compare this number. */
+int cf_context_generation(void);
 const char* cf_last_error(void);
 /* Number of kernels launched by this library since cf_init (for bench accounting). */
 uint64_t cf_launch_count(void);
@@ -165,7 +176,7 @@ int cf_run_aad(const cf_model* mdl, const cf_product* prd, const cf_rng* rng,
  *   risk_tables [cf_table_adjoint_size][n_payoffs]  sum over paths of d payoff[k] / d table (NOT divided by N),
  *               table-major like the reference's matrix risks(nParam, nPay) (mcBase.h:764-770)
  * Dupire (with the time map) x Europeans runs one sweep per maturity accumulated by strike class
- * (cf_multi.cuh); other pairs run one aggregate sweep per payoff (at most 64 payoffs). */
+ * (cf_multi.cuh; fixed-point integer accumulation: bit-reproducible); other pairs run one aggregate sweep per payoff. */
 int cf_run_aad_multi(const cf_model* mdl, const cf_product* prd, const cf_rng* rng,
                      uint64_t first_path, uint64_t n_paths, double* payoff_sums, double* risk_tables);
 
@@ -185,6 +196,10 @@ size_t cf_plan_out_size(const cf_plan* plan, int aad);   /* doubles in d_out */
 /* Average duration in ms of the dominant (path) kernel over the launches since the last call
  * (CUDA events recorded on the launch stream), and the number of launches averaged. */
 int cf_plan_kernel_ms(cf_plan* plan, double* avg_ms, int* n_launches);
+/* Diagnostics (CF_DEBUG_TIMES=1 in the environment): globaltimer stamps in ns of the phases of the last Dupire fast-path
+ * launch, out[3][1024][8]: [0] forward, [1] reverse (per block: entry, tables staged, dependency met, live paths
+ * compacted, sweep done, block sum, tables combined), [2][block][0] = live paths of the block. */
+int cf_plan_debug_times(cf_plan* plan, unsigned long long* out);
 
 /* ------------------------------------------------------------------------------------------
  * RNG kernels exposed for bit-exact parity tests (Sobol::next/skipTo sobol.h:77-151,
@@ -203,16 +218,42 @@ int cf_mrg_numerators(const cf_rng* rng, int dim, uint64_t first_path, uint64_t 
 int cf_inv_normal(const double* p, double* out, uint64_t n);
 
 
+/* Host-buffer runs of a resident plan (same outputs as cf_run_value / cf_run_aad without re-uploading the tables);
+ * sharded over the devices of the context / the processes of the communicator like the one-shot runs. */
+int cf_plan_run_value(cf_plan* plan, uint64_t first_path, uint64_t n_paths, double* payoff_sums, double* per_path_payoffs);
+int cf_plan_run_aad(cf_plan* plan, const double* payoff_weights, uint64_t first_path, uint64_t n_paths,
+                    double* payoff_sums, double* agg_sum, double* table_adjoints,
+                    double* per_path_payoffs, double* per_path_agg);
+int cf_plan_run_aad_multi(cf_plan* plan, uint64_t first_path, uint64_t n_paths, double* payoff_sums, double* risk_tables);
+
 /* ------------------------------------------------------------------------------------------
- * Multi-GPU (one process per GPU, paths sharded by [first_path, first_path + n_paths) per rank; mcBase.h has no
- * counterpart: its workers share one address space and add their risks in mcBase.h:737-746).
- * After this call the final reduction kernel of cf_plan_launch_aad / _value also sums over the ranks, through
- * peer memory: peer_bufs[r] is rank r's receive buffer (2 * world * cf_plan_out_size doubles) and peer_flags[r] its flag
- * words (world uint32, zero-initialised), both mapped into this process (CUDA IPC / symmetric memory); every rank
- * must then launch the same sequence of runs.  d_out receives the global sums, bit-identical on every rank.
- * world <= 1 switches the exchange off.  Dupire fast path only.
+ * Multi-GPU with one process per GPU.  mcBase.h has no counterpart: its workers share one address space and add
+ * their risks in a loop (mcBase.h:737-746, multi: 976-984).  The participants' sum of the result vector -- the
+ * path's only exchange step -- is done over peer memory inside the final reduction kernels (cf_comm.cuh), not by a
+ * collective call:
+ *   1. every process: cf_init(1, {its device}); cf_comm_create(world, rank, capacity, handle) allocates its receive
+ *      block (2 * world * capacity doubles + flags) and returns a CUDA IPC handle of CF_COMM_HANDLE_BYTES bytes;
+ *   2. the launcher gathers the handles in rank order (any transport: torch.distributed, MPI, a file);
+ *   3. every process: cf_comm_connect(all handles).
+ * From then on every run sums over the participants: cf_run_* / cf_plan_run_* take the WHOLE path range and run this
+ * process's shard of it (cf_shard_range); cf_plan_launch_* run the caller's own range.  Every participant must issue
+ * the same sequence of runs; all end with bit-identical sums.  capacity >= the longest result vector
+ * (cf_plan_out_size; n_payoffs * (1 + cf_table_adjoint_size) for cf_run_aad_multi).
+ * cf_comm_enable(0) keeps the communicator but makes launches local again (the caller reduces, e.g. with NCCL).
+ * A participant that never shows up makes the others return NaN after ~10 s and cf_comm_status() non-zero
+ * (the next call fails with that message) instead of hanging.
  * ---------------------------------------------------------------------------------------- */
-int cf_plan_set_peers(cf_plan* plan, int world, int rank, void* const* peer_bufs, void* const* peer_flags);
+#define CF_COMM_HANDLE_BYTES 64
+int cf_comm_create(int world, int rank, size_t capacity_doubles, void* handle_out);
+int cf_comm_connect(const void* handles /* [world][CF_COMM_HANDLE_BYTES] */);
+int cf_comm_enable(int on);
+int cf_comm_destroy(void);
+int cf_comm_info(int* world, int* rank, int* enabled);
+int cf_comm_status(void);
+/* Shard of participant `rank` of `world` over n_paths paths: boundaries on multiples of 256 paths (one Sobol window)
+ * and even (an antithetic pair of mrg32k3a is never split, as the reference's 64-path batches guarantee,
+ * mcBase.h:312); the last participant takes the remainder. */
+int cf_shard_range(uint64_t n_paths, int rank, int world, uint64_t* first, uint64_t* count);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): scalar FP64 DFMA peak of the bound device in TFLOP/s

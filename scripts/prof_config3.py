@@ -46,3 +46,25 @@ print("step ms (incl. reduction) median %.4f min %.4f" % (step_ms[len(step_ms) /
 ms = C.c_double(); nl = C.c_int()
 eng._chk(eng.lib.cf_plan_kernel_ms(plan, C.byref(ms), C.byref(nl)))
 print(mode, "kernel avg ms", ms.value, "paths/s %.4g" % (N / ms.value * 1e3), "fp64 peak TF", eng.fp64_peak_tflops())
+if os.environ.get("CF_DEBUG_TIMES"):
+    buf = np.zeros((3, 1024, 8), dtype=np.uint64)
+    eng._chk(eng.lib.cf_plan_debug_times(plan, buf.ctypes.data_as(C.c_void_p)))
+    nb = 148
+    f, r, lv = buf[0, :nb].astype(np.int64), buf[1, :nb].astype(np.int64), buf[2, :nb, 0].astype(np.int64)
+    t0 = f[:, 0].min()
+    def stat(name, x):
+        print("  %-34s min %8.1f  mean %8.1f  max %8.1f us" % (name, x.min() / 1e3, x.mean() / 1e3, x.max() / 1e3))
+    stat("fwd entry (since first entry)", f[:, 0] - t0)
+    stat("fwd tables staged", f[:, 1] - f[:, 0])
+    stat("fwd units done", f[:, 2] - f[:, 1])
+    stat("fwd end (since first entry)", f[:, 3] - t0)
+    if r[:, 0].max() > 0:
+        stat("rev entry (since fwd first entry)", r[:, 0] - t0)
+        stat("rev tables staged", r[:, 1] - r[:, 0])
+        stat("rev dependency wait", r[:, 2] - r[:, 1])
+        stat("rev live compaction", r[:, 3] - r[:, 2])
+        stat("rev sweep", r[:, 4] - r[:, 3])
+        stat("rev block sum + barrier", r[:, 5] - r[:, 4])
+        stat("rev combine tables", r[:, 6] - r[:, 5])
+        stat("rev end (since fwd first entry)", r[:, 6] - t0)
+        print("  live paths per block: min %d mean %.1f max %d" % (lv.min(), lv.mean(), lv.max()))

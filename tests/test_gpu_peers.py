@@ -1,4 +1,4 @@
-"""Two ranks on two GPUs: the sum over ranks done by the reduction kernel itself over peer memory (cf_plan_set_peers)
+"""Two ranks on two GPUs: the sum over ranks done by the reduction kernel itself over peer memory (cf_comm_create / cf_comm_connect: CUDA IPC)
 against one NCCL all-reduce of the per-rank results, and against the single-GPU numbers.  Needs two GPUs; skipped
 on a single-GPU box (the host-side sharding logic is covered on CPU by tests/test_dist.py)."""
 import json
@@ -28,5 +28,6 @@ def test_fused_reduction_over_two_ranks():
     d = json.loads(lines[0])
     # bench.py itself compares the fused result with one NCCL all-reduce of the per-rank vectors before using it
     assert "inside the reduction kernel" in d["config"]["parallelism"]
+    assert d["e2e"]["api"] == "dupireAADRisk (libcf_host.so)"                      # every rank calls the host API; the library shards
     assert abs(d["config"]["price"] / 0.96926107424976005 - 1) < 1e-10 and abs(d["config"]["delta"] / 0.020804057371458962 - 1) < 1e-8
     assert d["n_gpus"] == 2 and d["scaling"] == "strong"

@@ -87,6 +87,14 @@ struct Worker {
         state.store(0, std::memory_order_release);
         if (err) std::rethrow_exception(err);
     }
+    void stop()
+    {
+        if (!th.joinable()) return;
+        { std::lock_guard<std::mutex> lk(m); state.store(3, std::memory_order_release); }
+        cv.notify_all();
+        th.join();
+    }
+    ~Worker() { stop(); }
 };
 
 struct DeviceCtx {
@@ -136,6 +144,9 @@ std::unique_ptr<DeviceCtx> open_device(int id, int index, bool withWorker)
     if (withWorker) {
         CF_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
         if (index > 0) {
+            // the worker threads are stopped before the process tears the CUDA runtime down
+            static const bool registered = [] { std::atexit([] { for (auto& dd : g_devs) if (dd->worker) dd->worker->stop(); }); return true; }();
+            (void)registered;
             d->worker = std::make_unique<Worker>();
             d->worker->th = std::thread(worker_main, d.get());
         }
@@ -149,11 +160,7 @@ void close_devices()
 {
     retire_plans();
     for (auto& d : g_devs) {
-        if (d->worker) {
-            { std::lock_guard<std::mutex> lk(d->worker->m); d->worker->state.store(3); }
-            d->worker->cv.notify_all();
-            d->worker->th.join();
-        }
+        if (d->worker) d->worker->stop();
         cudaSetDevice(d->id);
         cudaDeviceSynchronize();
         if (d->stream) cudaStreamDestroy(d->stream);

@@ -332,6 +332,10 @@ inline CfSession* cfAcquireSession(const Product<T>& prd, const Model<T>& mdl, c
                   return s->key.contextGen != key->contextGen;
               }), all.end());
     if (all.size() >= 16) all.erase(all.begin());
+    // the sessions hold device plans: they are released at exit while the CUDA runtime is still up (exit handlers run in
+    // reverse order of registration; the runtime registered its own before the plan above could be created)
+    static const bool atExit = [] { std::atexit([] { cfSessions().clear(); }); return true; }();
+    (void)atExit;
     all.push_back(std::move(fresh));
     return all.back().get();
 }

@@ -21,7 +21,7 @@ def _gpus():
 def test_entry_points_on_two_devices_match_one_device(built):
     n = min(_gpus(), 4)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "multidev_check.py"), str(n)], cwd=ROOT, capture_output=True,
-                         text=True, timeout=900)
+                         text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("MULTIDEV ")][0]
     rep = json.loads(line[len("MULTIDEV "):])

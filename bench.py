@@ -176,17 +176,156 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---- the other BASELINE configs (parity-test cases at their full sizes): `--config 1|2|4|5` prints the same kind of line
+#      for them, through the reference-facing host API; flops per path by SURVEY.md 8d
+def _put_config(api, k):
+    a = np.arange(10)
+    s5 = 100.0 + 5 * a
+    spots, times, vols = config3()
+    if k in (1, 2):
+        (api.put_black_scholes if hasattr(api, "put_black_scholes") else api.put_bs)(100.0, 0.15, False, 0.0, 0.0, "bench_bs")
+        if k == 1:
+            api.put_european(100.0, 1.0, 1.0, "bench_prd")
+        else:
+            api.put_barrier(100.0, 120.0, 1.0, 1.0 / 52, 0.01, False, "bench_prd")
+        return "bench_bs"
+    if k == 4:
+        api.put_dupire(100.0, spots, times, vols, 0.25, "bench_dup4")
+        api.put_europeans(np.repeat(0.25 * np.arange(1, 13), 60), np.tile(70.5 + np.arange(60), 12), "bench_prd")
+        return "bench_dup4"
+    api.put_displaced(s5, 0.20 + 0.02 * a, np.where(a % 3 == 0, 0.0, -0.05 * (a % 3)), 0.02, 0.001 * a, [0.5, 1.5],
+                      np.full((2, 10), 0.01), np.full((10, 10), 0.5) + 0.5 * np.eye(10), 0.25, "bench_dlm")
+    api.put_autocall(s5, 3.0, 12, 1.0, 0.7, 0.10, 0.01, "bench_prd")
+    return "bench_dlm"
+
+
+CONFIGS = {
+    # paths, sobol, flops per path, workload, entry point, CPU sample
+    1: (1 << 16, True, 1.5e2, "bs_european_2^16_sobol_paths_aad_4_risks", "AADriskOne", 1 << 16),
+    2: (1 << 20, True, 5.0e3, "bs_uoc_barrier_2^20_sobol_paths_x_52_steps_aad_4_risks", "AADriskOne", 1 << 18),
+    4: (1 << 22, False, 3.8e3, "dupire_europeans_720_payoffs_2^22_mrg32k3a_paths_x_12_steps_aad_multi_1081x720", "AADriskMulti", 1 << 12),
+    5: (1 << 22, False, 1.2e4, "displaced_10_assets_autocall_2^22_mrg32k3a_paths_x_12_periods_aad_107_risks", "AADriskOne", 1 << 17),
+}
+
+
+def _call_config(api, k, model, n, sobol):
+    if k == 4:
+        return api.aad_risk_multi(model, "bench_prd", n, sobol=sobol)
+    return api.aad_risk_one(model, "bench_prd", n, sobol=sobol)
+
+
+def run_config(args):
+    """One of the secondary configs through the host API.  N > 1: every rank calls the entry point with the full path
+    count; the library runs the rank's shard and sums over the ranks inside its kernels (IPC communicator)."""
+    import torch
+    import torch.distributed as dist
+    from compfinance_b200 import capi
+    from compfinance_b200.api import CompFinance
+    k = args.config
+    n_paths, sobol, flops, workload, entry, cpu_sample = CONFIGS[k]
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cf = CompFinance(device=local_rank)
+    eng = capi.Engine()
+    model = _put_config(cf, k)
+    if world > 1:
+        from compfinance_b200.dist import connect_comm
+        n_par = cf.num_params(model)
+        n_pay = cf.num_payoffs("bench_prd")
+        connect_comm(eng, max(4096, n_pay * (n_par + 600)))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    res = None
+    for _ in range(args.warmup):
+        res = _call_config(cf, k, model, n_paths, sobol)
+    torch.cuda.synchronize()
+    launches0 = eng.lib.cf_launch_count()
+    sampler.mark()
+    if world > 1:
+        dist.barrier()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    t_tot, kms = 0.0, []
+    for _ in range(args.steps):
+        flush.fill_(1)                                           # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        res = _call_config(cf, k, model, n_paths, sobol)
+        t_tot += time.perf_counter() - t0
+        kms.append(eng.lib.cf_last_run_kernel_ms())
+    tt = torch.tensor([t_tot], dtype=torch.float64, device="cuda")
+    km = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(km, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()
+    launches = eng.lib.cf_launch_count() - launches0
+    if rank == 0:
+        e2e_value = n_paths * args.steps / float(tt.item())
+        kernel_ms = float(km.item())
+        value = n_paths / (kernel_ms * 1e-3)                     # device time of the path kernels (max over ranks)
+        fp64_peak = eng.fp64_peak_tflops()
+        achieved = value * flops / 1e12
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                from oracle import refapi
+                ref = refapi.get()
+                threads = ref.start_pool(-1) + 1
+                rmodel = _put_config(ref, k)
+                _call_config(ref, k, rmodel, min(cpu_sample, 1 << 12), sobol)
+                t0 = time.perf_counter()
+                _call_config(ref, k, rmodel, cpu_sample, sobol)
+                secs = time.perf_counter() - t0
+                cpu = {"value": cpu_sample / secs, "unit": "paths/s", "cores": threads, "kind": "reference",
+                       "sample": f"{cpu_sample} paths of the same workload through {entry}"}
+            except (OSError, FileNotFoundError) as ex:
+                cpu = {"value": None, "unit": "paths/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+        values = np.asarray(res[0]).ravel()
+        line = {
+            "metric": "paths_per_sec_incl_full_aad_risk", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "baseline_config": k, "paths": n_paths, "rng": "sobol" if sobol else "mrg32k3a", "entry_point": entry,
+                       "parallelism": f"paths sharded over {world} GPU(s)" + (", rank sum over peer memory inside the reduction kernels" if world > 1 else ""),
+                       "l2": "flushed between timed iterations (256 MB write)", "first_payoff_value": float(values[0])},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": 8 * cf.num_payoffs("bench_prd"),
+                    "d2h_bytes_per_step": 8 * int(sum(np.asarray(r).size for r in res if not np.isscalar(r))), "steps": args.steps,
+                    "api": f"{entry} (libcf_host.so)", "regime": "resident session"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         "traffic": None, "kernel_ms": kernel_ms, "algorithmic_flops_per_path": flops,
+                         "peak_source": "measured here: scalar DFMA microbenchmark cf_measure_fp64_peak",
+                         "note": "value and kernel_ms are the device time of the path kernels of the call (CUDA events on the launch stream, max over ranks); e2e is the wall time of the call"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE config: 3 (default) is the headline; the others are the parity configs at their full sizes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.config != 3:
+        args.steps = min(args.steps, 20)
+        run_config(args)
         return
 
     import torch

@@ -69,6 +69,7 @@ def load():
     lib.cf_plan_run_value.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _dp, _dp]
     lib.cf_plan_run_aad.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, _dp]
     lib.cf_plan_run_aad_multi.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _dp, _dp]
+    lib.cf_last_run_kernel_ms.restype = C.c_double
     lib.cf_comm_create.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p]
     lib.cf_comm_connect.argtypes = [C.c_void_p]
     lib.cf_comm_enable.argtypes = [C.c_int]
@@ -91,10 +92,10 @@ def load():
 EXPORTED = [
     "cf_init", "cf_shutdown", "cf_last_error", "cf_launch_count", "cf_table_adjoint_size", "cf_run_value",
     "cf_run_aad", "cf_run_aad_multi", "cf_plan_create", "cf_plan_destroy", "cf_plan_launch_value", "cf_plan_launch_aad",
-    "cf_plan_out_size", "cf_plan_kernel_ms", "cf_plan_run_value", "cf_plan_run_aad", "cf_plan_run_aad_multi", "cf_plan_debug_times", "cf_device_count", "cf_context_generation",
+    "cf_plan_out_size", "cf_plan_kernel_ms", "cf_plan_run_value", "cf_plan_run_aad", "cf_plan_run_aad_multi", "cf_last_run_kernel_ms", "cf_plan_debug_times", "cf_device_count", "cf_context_generation",
     "cf_comm_create", "cf_comm_connect", "cf_comm_enable", "cf_comm_destroy", "cf_comm_info", "cf_comm_status", "cf_shard_range",
     "cf_sobol_states", "cf_sobol_direction_number", "cf_sobol_max_dim",
-    "cf_rng_draw", "cf_mrg_numerators", "cf_inv_normal", "cf_measure_fp64_peak", "cf_device_sm_count",
+    "cf_rng_draw", "cf_mrg_numerators", "cf_inv_normal", "cf_selftest_mrg_uniform", "cf_measure_fp64_peak", "cf_device_sm_count",
 ]
 
 

@@ -359,7 +359,9 @@ void validate(const cf_model* mdl, const cf_product* prd, const cf_rng* rng)
     } else if (rng->kind != CF_RNG_MRG32K3A) throw CfError("cf_b200: unknown RNG kind");
 }
 
-// ---- the participants of the rank sum (cf_comm.cuh): the devices of this context, or one device per process
+// ---- the participants of the rank sum (cf_comm.cuh): the devices of this context, or one device per process.
+// A receive block is 2 x world x capacity slots of 16 bytes (256 MB per device for 8 participants at the default
+// capacity of 2^20 doubles, CF_COMM_CAPACITY)
 struct CommState {
     int world = 0;                        // participants, 0: no communicator
     int rank0 = 0;                        // rank of local device 0 (local device k is participant rank0 + k)
@@ -369,24 +371,19 @@ struct CommState {
     uint32_t epoch = 0;                   // exchanges so far, the same on every participant
     long long timeout = 20000000000ll;    // clocks (~10 s) a participant waits for its peers
     std::vector<unsigned char*> local;    // receive block of each local device (cudaMalloc)
-    std::vector<uint32_t*> ticket;        // per local device
     std::vector<void*> opened;            // remote blocks opened through IPC
     unsigned char* block[cf::kMaxPeers] = {};   // receive block of participant r as addressable from this process
     int* status = nullptr;                // mapped pinned host word: epoch of an exchange that timed out, 0: none
     int* statusDev = nullptr;
 
-    size_t rowBytes() const { return size_t(2) * size_t(world) * cap * sizeof(double); }
-    size_t blockBytes() const { return rowBytes() + 256; }
+    size_t blockBytes() const { return size_t(2) * size_t(world) * cap * sizeof(cf::PeerSlot); }
     bool on() const { return world > 1 && enabled; }
     cf::DPeers peers(int localIndex, uint32_t ep) const
     {
         cf::DPeers p{};
         p.world = world; p.rank = rank0 + localIndex; p.epoch = ep; p.cap = cap; p.timeout = timeout;
-        for (int r = 0; r < world; ++r) {
-            p.buf[r] = reinterpret_cast<double*>(block[r]);
-            p.flag[r] = reinterpret_cast<uint32_t*>(block[r] + rowBytes());
-        }
-        p.ticket = ticket[size_t(localIndex)];
+        (void)localIndex;
+        for (int r = 0; r < world; ++r) p.buf[r] = reinterpret_cast<cf::PeerSlot*>(block[r]);
         p.status = statusDev;
         return p;
     }
@@ -406,7 +403,6 @@ void comm_destroy()
     for (size_t k = 0; k < g_comm.local.size(); ++k) {
         if (k < g_devs.size()) cudaSetDevice(g_devs[k]->id);
         if (g_comm.local[k]) cudaFree(g_comm.local[k]);
-        if (g_comm.ticket[k]) cudaFree(g_comm.ticket[k]);
     }
     if (g_comm.status) cudaFreeHost(g_comm.status);
     g_comm = CommState{};
@@ -426,13 +422,10 @@ void comm_allocate(int world, int rank0, size_t cap)
     for (auto& d : g_devs) {
         DeviceScope sc(d.get());
         unsigned char* b = nullptr;
-        uint32_t* t = nullptr;
         CF_CUDA(cudaMalloc(reinterpret_cast<void**>(&b), g_comm.blockBytes()));
         CF_CUDA(cudaMemset(b, 0, g_comm.blockBytes()));
-        CF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t), sizeof(uint32_t)));
-        CF_CUDA(cudaMemset(t, 0, sizeof(uint32_t)));
         CF_CUDA(cudaDeviceSynchronize());
-        g_comm.local.push_back(b); g_comm.ticket.push_back(t);
+        g_comm.local.push_back(b);
     }
 }
 
@@ -479,8 +472,8 @@ struct DevPlan {
     DevBuf<uint32_t> stepBits;
     DevBuf<int32_t> k12;
     DevBuf<uint8_t> flushOps;
-    DevBuf<double2> spanW;            // span reverse kernel: per step time weights, packed columns / phases, phases per round
-    DevBuf<uint32_t> spanPack, spanNph;
+    DevBuf<double2> spanW;            // span reverse kernel: per step (padded) time weights and column offsets of its two targets
+    DevBuf<uint2> spanOff;
     int spanS = 0;                    // steps per lane; 0: the span kernel cannot run this plan
     int nCells = 0;
     cf::DArgs dbase{};
@@ -520,7 +513,7 @@ struct DevPlan {
     void exchange(const double* dLocal, int nOut, double* dOut, const cf::DPeers& px, cudaStream_t s)
     {
         if (size_t(nOut) > px.cap) throw CfError("cf_b200: result vector longer than the communicator's capacity");
-        const int block = 256, grid = std::max(1, std::min(dev->sms, (nOut + block - 1) / block));
+        const int block = 256, grid = std::max(1, std::min(4 * dev->sms, (nOut + block - 1) / block));
         cf::peer_exchange_kernel<<<grid, block, 0, s>>>(dLocal, nOut, dOut, px);
         CF_CUDA(cudaGetLastError());
         ++g_launches;
@@ -735,7 +728,7 @@ struct DevPlan {
 
     // The reverse sweep has two forms (cf_dupire.cuh): classic (one path per lane, 8 warps: many live paths per SM) and
     // span (one warp per live path, a lane per S consecutive steps, 16 warps: few live paths per SM, the shard of a
-    // multi-GPU run).  Measured cross-over: about 1500 paths per SM.  CF_DUPIRE_REV = span | classic forces one.
+    // multi-GPU run).  Measured cross-over: about 1300 paths per SM.  CF_DUPIRE_REV = span | classic forces one.
     enum { kRevSpan = 0, kRevClassic = 2 };
     int reverseForm(uint64_t nPad) const
     {
@@ -743,8 +736,9 @@ struct DevPlan {
             const char* e = std::getenv("CF_DUPIRE_REV");
             return !e ? -1 : (std::strcmp(e, "classic") == 0 ? int(kRevClassic) : (std::strcmp(e, "span") == 0 ? int(kRevSpan) : -1));
         }();
-        int form = forced >= 0 ? forced : (nPad <= uint64_t(g_sms) * 1536 ? int(kRevSpan) : int(kRevClassic));
-        if (form == kRevSpan && spanS == 0) form = kRevClassic;
+        int form = forced >= 0 ? forced : (nPad <= uint64_t(g_sms) * 1280 ? int(kRevSpan) : int(kRevClassic));
+        // the span kernel's blocks scan the live mask of the whole launch
+        if (form == kRevSpan && (spanS == 0 || nPad / 32 > uint64_t(cf::kRevSMaxWords))) form = kRevClassic;
         return form;
     }
 
@@ -778,8 +772,9 @@ struct DevPlan {
         const bool span = form == kRevSpan;
         const int revWarps = span ? cf::kRevSWarps : cf::kRevWarps;
         const int revMaxWords = span ? cf::kRevSMaxWords : cf::kRevMaxWords;
-        // reverse blocks own contiguous ranges of live-mask words (32 paths each), at most revMaxWords per block
-        const int minGridR = int((maxPad / 32 + revMaxWords - 1) / revMaxWords);
+        // classic: reverse blocks own contiguous ranges of live-mask words (32 paths each), at most revMaxWords per block;
+        // span: equal shares of the live paths of the launch, one block per SM
+        const int minGridR = span ? 1 : int((maxPad / 32 + revMaxWords - 1) / revMaxWords);
         const int gridR = std::max(int(std::min<uint64_t>(maxPad / 32, uint64_t(g_sms))), minGridR);
         const size_t tabLen = size_t(nTimes) * m;
         scratch.need(scratch.partial, size_t(gridF) * (size_t(nPay) + 1), s);
@@ -800,7 +795,7 @@ struct DevPlan {
               : fwdCh == cf::kFwdChunk ? cf::dupire_smem_fwd4<1, cf::kFwdChunk>(D, m, dim, sob, nCells, fwdWarps).total
                                        : cf::dupire_smem_fwd4<1, cf::kFwdChunk1>(D, m, dim, sob, nCells, fwdWarps).total;
         auto rev = span ? cf::pick_dupire_reverse_span(prdKind, spanS) : cf::pick_dupire_reverse(prdKind);
-        const size_t smemR = span ? cf::dupire_smem_revs(D, m, nCells, nTimes).total : cf::dupire_smem_rev(D, m, nCells).total;
+        const size_t smemR = span ? cf::dupire_smem_revs(spanS, m, nCells, nTimes).total : cf::dupire_smem_rev(D, m, nCells).total;
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fwd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
         if (aad) CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rev), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemR)));
         static const bool dbgT = std::getenv("CF_DEBUG_TIMES") != nullptr;
@@ -915,6 +910,8 @@ std::unique_ptr<DevPlan> make_plan(const cf_model* mdl, const cf_product* prd, c
         cf::LArgs& l = p->lbase;
         l.A = p->A; l.D = p->D; l.E = p->E; l.today = mdl->is_event[0] ? 1 : 0;
         l.spots = p->lSpots.p; l.chol = p->lChol.p; l.alphas = p->lAlphas.p; l.dyn = p->lDyn.p;
+        for (int k = 0; k < p->A; ++k)
+            for (int j = 0; j <= k; ++j) l.cholv[k * (k + 1) / 2 + j] = mdl->dlm_chol[size_t(k) * p->A + j];
         l.dynFwd = p->lDynFwd.p; l.drifts = p->lDrifts.p; l.stds = p->lStds.p; l.ff = p->lFf.p; l.num = p->lNum.p;
         l.n_payoffs = prd->n_payoffs; l.n_strikes = prd->kind == CF_PRODUCT_BASKETS ? prd->n_payoffs : 0;
         l.strike = prd->strike; l.ko = prd->barrier; l.smooth = prd->smooth; l.coupon = prd->coupon;
@@ -1051,46 +1048,50 @@ std::unique_ptr<DevPlan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 p->k12.upload(colxy.data(), colxy.size());
                 p->flushOps.upload(ops.data(), ops.size());
                 // span reverse kernel: lane l sweeps steps [S l, S l + S); in round j the 32 lanes add to the time columns of
-                // steps S l + j.  Targets (step, column) get a phase such that no column is touched twice in a phase of a round.
+                // steps S l + j.  A step has up to two targets (column, weight); they are ordered (A, B) so that within a
+                // round no column is the A target of two lanes, nor the B target of two lanes.
                 {
                     const int S = cf::dupire_span_steps(D);
-                    std::vector<double2> sw(static_cast<size_t>(D));
-                    std::vector<uint32_t> pack(static_cast<size_t>(D), 0u), nph(8, 1u);
+                    const int Dp = 32 * S;
+                    std::vector<double2> sw(static_cast<size_t>(std::max(Dp, 1)), make_double2(0.0, 0.0));
+                    const uint32_t rowBytes = uint32_t(sizeof(double) * cf::kRevSRow);
+                    const uint32_t sink = uint32_t(p->nTimes) * rowBytes;       // absent targets (and padding steps) add 0 to a row nobody reads
+                    std::vector<uint2> off(static_cast<size_t>(std::max(Dp, 1)), make_uint2(sink, sink));
                     bool ok = S > 0 && p->hasTimeMap && p->nTimes <= 255
-                              && cf::dupire_smem_revs(D, m, nCells, p->nTimes).total <= kFastSmemLimit;
+                              && cf::dupire_smem_revs(S, m, nCells, p->nTimes).total <= kFastSmemLimit;
                     for (int j = 0; ok && j < S; ++j) {
-                        std::vector<std::vector<int>> used(cf::kRevSMaxPhases);
-                        auto place = [&](int col, int notPhase) {
-                            for (int ph = 0; ph < cf::kRevSMaxPhases; ++ph)
-                                if (ph != notPhase && std::find(used[size_t(ph)].begin(), used[size_t(ph)].end(), col) == used[size_t(ph)].end()) {
-                                    used[size_t(ph)].push_back(col);
-                                    return ph;
-                                }
-                            return -1;
-                        };
-                        int phases = 1;
+                        std::vector<int> usedA, usedB;
+                        auto free_ = [](const std::vector<int>& used, int col) { return std::find(used.begin(), used.end(), col) == used.end(); };
                         for (int l = 0; l < 32 && ok; ++l) {
                             const int i = S * l + j;
                             if (i >= D) break;
                             int c1 = mdl->time_col1[i], c2 = mdl->time_col2[i];
                             double v1 = mdl->time_w1[i], v2 = mdl->time_w2[i];
                             if (c2 == c1) { v1 += v2; v2 = 0.0; }
-                            const bool has2 = v2 != 0.0;
-                            const int ph1 = place(c1, -1), ph2 = has2 ? place(c2, ph1) : 0;     // a step's two targets never share a phase
-                            if (ph1 < 0 || ph2 < 0) { ok = false; break; }
-                            phases = std::max(phases, std::max(ph1, ph2) + 1);
-                            sw[size_t(i)] = make_double2(v1, v2);
-                            pack[size_t(i)] = uint32_t(c1) | (uint32_t(has2 ? c2 : c1) << 8) | (uint32_t(ph1) << 16) | (uint32_t(ph2) << 18)
-                                              | (has2 ? cf::DSpanStep::kHas2 : 0u)
-                                              | ((i + 1 < D && mdl->is_event[i + 1]) ? cf::DSpanStep::kEvent : 0u);
+                            const bool two = v2 != 0.0;
+                            int cA = -1, cB = -1;
+                            double vA = 0.0, vB = 0.0;
+                            if (two) {
+                                if (free_(usedA, c1) && free_(usedB, c2)) { cA = c1; vA = v1; cB = c2; vB = v2; }
+                                else if (free_(usedA, c2) && free_(usedB, c1)) { cA = c2; vA = v2; cB = c1; vB = v1; }
+                                else ok = false;
+                            } else {
+                                if (free_(usedA, c1)) { cA = c1; vA = v1; }
+                                else if (free_(usedB, c1)) { cB = c1; vB = v1; }
+                                else ok = false;
+                            }
+                            if (!ok) break;
+                            if (cA >= 0) usedA.push_back(cA);
+                            if (cB >= 0) usedB.push_back(cB);
+                            sw[size_t(i)] = make_double2(vA, vB);
+                            off[size_t(i)] = make_uint2((cA >= 0 ? uint32_t(cA) * rowBytes : sink) | ((i + 1 < D && mdl->is_event[i + 1]) ? cf::kSpanEvent : 0u),
+                                                        cB >= 0 ? uint32_t(cB) * rowBytes : sink);
                         }
-                        nph[size_t(j)] = uint32_t(phases);
                     }
                     if (ok) {
                         p->spanS = S;
                         p->spanW.upload(sw.data(), sw.size());
-                        p->spanPack.upload(pack.data(), pack.size());
-                        p->spanNph.upload(nph.data(), nph.size());
+                        p->spanOff.upload(off.data(), off.size());
                     }
                 }
                     const bool sob = rng->kind == CF_RNG_SOBOL;
@@ -1122,7 +1123,7 @@ std::unique_ptr<DevPlan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 d.ab = p->ab.p; d.yrows = p->tabA.p; d.bk = p->bk.p; d.cells = p->cells.p; d.n_cells = nCells;
                 d.cell_scale = scale; d.cell_off = -x0 * scale;
                 d.wxy = p->c12.p; d.colxy = p->k12.p; d.flush_ops = p->flushOps.p;
-                d.span_w = p->spanW.p; d.span_pack = p->spanPack.p; d.span_nph = p->spanNph.p; d.span_S = p->spanS;
+                d.span_w = p->spanW.p; d.span_off = p->spanOff.p; d.span_S = p->spanS;
                 d.n_payoffs = prd->n_payoffs; d.is_put = prd->is_put;
                 d.strike = prd->strike; d.barrier = prd->barrier; d.smooth = prd->smooth;
             }
@@ -1237,6 +1238,15 @@ __global__ void inv_normal_kernel(const double* __restrict__ p, double* __restri
     if (i < n) out[i] = cf::inv_normal_cdf(p[i]);
 }
 
+
+// every 32-bit numerator: the lean quotient of mrg_uniform against the IEEE division
+__global__ void mrg_uniform_selftest_kernel(unsigned long long* mismatches)
+{
+    unsigned long long bad = 0;
+    for (unsigned long long z = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; z < (1ull << 32); z += uint64_t(gridDim.x) * blockDim.x)
+        if (cf::mrg_uniform(uint32_t(z)) != cf::mrg_uniform_ieee(uint32_t(z))) ++bad;
+    if (bad) atomicAdd(mismatches, bad);
+}
 
 // FP64 peak microbenchmark: 8 independent DFMA chains per thread (roofline denominator of bench.py)
 __global__ void fp64_peak_kernel(double* out, int iters, double a, double b)
@@ -1378,6 +1388,7 @@ void on_devices(int nLocal, F&& job)
 }
 
 enum class RunKind { Value, Aad, Multi };
+double g_lastKernelMs = 0.0;
 
 // One run of a plan over paths [first, first + n) with host results.  With a communicator the range is sharded over
 // its participants -- the devices of this context, or this process's device among the processes of the job -- and the
@@ -1421,6 +1432,12 @@ void run_plan(cf_plan& mp, RunKind kind, const double* w, uint64_t first, uint64
     on_devices(nLocal, job);
     g_comm.check();
     std::memcpy(hOut, pinned, sizeof(double) * nOut);
+    // device time of the path kernels of this run on the first local device (cf_last_run_kernel_ms)
+    if (!p0.events.empty()) {
+        float ms = 0.f;
+        const auto& ev = p0.events.back();
+        if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) g_lastKernelMs = ms;
+    }
 }
 
 }  // namespace
@@ -1620,6 +1637,8 @@ int cf_plan_run_aad(cf_plan* plan, const double* payoff_weights, uint64_t first_
     });
 }
 
+double cf_last_run_kernel_ms(void) { return g_lastKernelMs; }
+
 int cf_plan_debug_times(cf_plan* plan, unsigned long long* out /* [3][1024][8] */)
 {
     return guarded([&] {
@@ -1779,6 +1798,22 @@ int cf_measure_fp64_peak(double* tflops, double* ms_out)
         const double flops = double(grid) * block * 8.0 * iters * 2.0;
         if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
         if (ms_out) *ms_out = best;
+    });
+}
+
+int cf_selftest_mrg_uniform(uint64_t* mismatches)
+{
+    return guarded([&] {
+        ensure_init();
+        if (!mismatches) throw CfError("cf_selftest_mrg_uniform: null argument");
+        DevBuf<unsigned long long> d; d.alloc(1);
+        CF_CUDA(cudaMemset(d.p, 0, sizeof(unsigned long long)));
+        mrg_uniform_selftest_kernel<<<g_sms * 8, 256>>>(d.p);
+        ++g_launches;
+        CF_CUDA(cudaGetLastError());
+        unsigned long long h = 0;
+        CF_CUDA(cudaMemcpy(&h, d.p, sizeof(h), cudaMemcpyDeviceToHost));
+        *mismatches = h;
     });
 }
 

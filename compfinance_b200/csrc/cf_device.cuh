@@ -180,7 +180,11 @@ struct MrgThread {
     }
 };
 
-__device__ __forceinline__ double mrg_uniform(uint32_t z) { return double(z) / 4294967088.0; }
+__device__ __forceinline__ double div_fast(double a, double b);
+// u = z / (m1 + 1) (mrg32k3a.h:75-80); the lean quotient is bit for bit the IEEE one for every numerator z < 2^32
+// (checked exhaustively on the device: cf_selftest_mrg_uniform, tests/test_gpu_rng.py)
+__device__ __forceinline__ double mrg_uniform(uint32_t z) { return div_fast(double(z), 4294967088.0); }
+__device__ __forceinline__ double mrg_uniform_ieee(uint32_t z) { return double(z) / 4294967088.0; }
 
 // a / b for b > 0 where a is often exactly zero (adjoints of inactive branches, dead notionals, options out of the
 // money).  CUDA's double division leaves its inline path for a zero numerator and runs the out-of-line routine
@@ -188,6 +192,51 @@ __device__ __forceinline__ double mrg_uniform(uint32_t z) { return double(z) / 4
 __device__ __forceinline__ double div_z(double a, double b) { return a == 0.0 ? a : a / b; }
 // the same for a numeraire-like divisor that is often exactly 1 (models without rates leave the Sample default): a / 1 = a
 __device__ __forceinline__ double div_n(double a, double num) { return (a == 0.0 || num == 1.0) ? a : a / num; }
+
+// ---------------------------------------------------------------------------------------------
+// Lean arithmetic shared by the path kernels
+// ---------------------------------------------------------------------------------------------
+// a / b for normal operands well inside the exponent range: reciprocal seed (relative error < 2^-19.9, measured), one
+// cubic Newton step (r (1 + e + e^2): error ~ e^3 = 2^-60), one residual correction of the quotient.  CUDA's own
+// division adds a second Newton step and a range check; on 1.5e9 random operands of the ranges met here this
+// sequence returned the IEEE quotient every time (tools/micro/divtest.cu).
+__device__ __forceinline__ double div_fast(double a, double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+// exp(x) for |x| < 700 (no overflow / underflow / NaN handling): x = k ln 2 + r, |r| <= ln 2 / 2, Taylor to r^13 (2e-18),
+// the exponent added to the high word.  Error < 1 ulp like the library exp; used on the few samples inside the barrier's
+// log-space pre-filter, where the library routine's range handling is most of the cost.
+__device__ __forceinline__ double exp_core(double x)
+{
+    const double kd = fma(x, 1.4426950408889634e+00, 6755399441055744.0);      // round to nearest: k in the low word
+    const int k = __double2loint(kd);
+    const double kf = kd - 6755399441055744.0;
+    double r = fma(kf, -6.93147180559945286227e-01, x);
+    r = fma(kf, -2.31904681384629955842e-17, r);
+    double p = 1.60590438368216145994e-10;                                      // 1 / 13!
+    p = fma(p, r, 2.08767569878680989792e-09);
+    p = fma(p, r, 2.50521083854417187751e-08);
+    p = fma(p, r, 2.75573192239858906526e-07);
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
 
 // ---------------------------------------------------------------------------------------------
 // Deterministic reductions

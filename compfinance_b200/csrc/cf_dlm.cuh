@@ -33,6 +33,8 @@ struct LArgs {
     int      A, D, E, today;       // assets, steps, events; today = 1 when timeline point 0 is an event date
     const double*  spots;          // [A]
     const double*  chol;           // [A][A] lower
+    double         cholv[136];     // the same lower triangle, row k at k (k + 1) / 2: kernel parameters live in the constant bank,
+                                   // so the correlation sums read their coefficients as instruction operands, not through loads
     const double*  alphas;         // [A]
     const int32_t* dyn;            // [A] 0 lognormal 1 normal 2 surnormal 3 subnormal
     const double*  dynFwd;         // [D][A]
@@ -191,10 +193,10 @@ __global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(
 #pragma unroll
             for (int k = 0; k < AMAX; ++k) F[k] = (k < A) ? S[k] * __ldg(a.ff + e * A + k) : 0.0;
             if (PRD == CF_PRODUCT_AUTOCALL) {
-                double worst = F[0] / __ldg(a.pweights);
+                double worst = div_fast(F[0], __ldg(a.pweights));
 #pragma unroll
                 for (int k = 1; k < AMAX; ++k)
-                    if (k < A) { const double pf = F[k] / __ldg(a.pweights + k); if (pf < worst) worst = pf; }
+                    if (k < A) { const double pf = div_fast(F[k], __ldg(a.pweights + k)); if (pf < worst) worst = pf; }
                 pay += div_z(alive * a.coupon * a.cpn_dt, num);
                 if (e < E - 1) {
                     const double f = fmin(1.0, fmax(0.0, (a.ko + a.smooth - worst) / 2 / a.smooth));
@@ -248,15 +250,16 @@ __global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(
                 if (k < A) {
                     double cw = 0.0;
 #pragma unroll
-                    for (int j = 0; j <= k; ++j) cw += __ldg(a.chol + k * A + j) * w[j];
+                    for (int j = 0; j <= k; ++j) cw += a.cholv[k * (k + 1) / 2 + j] * w[j];
                     const double fwd = S[k] * __ldg(a.dynFwd + i * A + k);
                     const double sd = __ldg(a.stds + i * A + k), dr = __ldg(a.drifts + i * A + k);
                     const int dyn = __ldg(a.dyn + k);
                     const double al = __ldg(a.alphas + k);
-                    if (dyn == 0) S[k] = fwd * exp(dr + sd * cw);
+                    // exp_core: the library's accuracy (< 1 ulp) without its range handling; the exponent is a few standard deviations
+                    if (dyn == 0) S[k] = fwd * exp_core(dr + sd * cw);
                     else if (dyn == 1) S[k] = fwd + sd * cw;
-                    else if (dyn == 2) S[k] = (fwd + al) * exp(dr + sd * cw) - al;
-                    else S[k] = (fwd - al) * exp(dr + sd * cw) + al;
+                    else if (dyn == 2) S[k] = (fwd + al) * exp_core(dr + sd * cw) - al;
+                    else S[k] = (fwd - al) * exp_core(dr + sd * cw) + al;
                 }
             }
             if (AAD) {
@@ -286,11 +289,11 @@ __global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(
                 for (int k = 0; k < AMAX; ++k) { F[k] = (k < A) ? Sev[k] * __ldg(a.ff + ev * A + k) : 0.0; Fbar[k] = 0.0; }
                 double numbar = 0.0;
                 if (PRD == CF_PRODUCT_AUTOCALL) {
-                    double worst = F[0] / __ldg(a.pweights);
+                    double worst = div_fast(F[0], __ldg(a.pweights));
                     int am = 0;
 #pragma unroll
                     for (int k = 1; k < AMAX; ++k)
-                        if (k < A) { const double pf = F[k] / __ldg(a.pweights + k); if (pf < worst) { worst = pf; am = k; } }
+                        if (k < A) { const double pf = div_fast(F[k], __ldg(a.pweights + k)); if (pf < worst) { worst = pf; am = k; } }
                     double worstbar;
                     if (ev < E - 1) {
                         const double q = (a.ko + a.smooth - worst) / 2 / a.smooth;
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(
                     if (k < A) {
                         double cw = 0.0;
 #pragma unroll
-                        for (int j = 0; j <= k; ++j) cw += __ldg(a.chol + k * A + j) * w[j];
+                        for (int j = 0; j <= k; ++j) cw += a.cholv[k * (k + 1) / 2 + j] * w[j];
                         const double df = __ldg(a.dynFwd + i * A + k);
                         const double fwd = Sp[k] * df;
                         const double sd = __ldg(a.stds + i * A + k), dr = __ldg(a.drifts + i * A + k);
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(kBlock, (AAD && AMAX > 8) ? 1 : 2) dlm_kernel(
                         if (dyn == 1) {                               // S = fwd + std cw
                             fwdbar = sb; sdbar = sb * cw; cwbar = sb * sd;
                         } else {
-                            const double ex = exp(dr + sd * cw);
+                            const double ex = exp_core(dr + sd * cw);
                             fwdbar = sb * ex;
                             if (dyn == 0) xbar = sb * Sn[k];                                   // S = fwd e
                             else if (dyn == 2) { xbar = sb * (Sn[k] + al); alphaBar[k] += sb * (ex - 1.0); }   // S = (fwd + al) e - al

@@ -447,7 +447,7 @@ struct GaussGen {
             double r = x * x;
             const double num = ((-25.44106049637 * r + 41.39119773534) * r + -18.61500062529) * r + 2.50662823884;
             const double den = (((3.13082909833 * r + -21.06224101826) * r + 23.08336743743) * r + -8.47351093090) * r + 1.0;
-            r = x * num / den;
+            r = div_fast(x * num, den);                 // den in [0.11, 1]: the lean quotient equals the IEEE one (cf_device.cuh)
             gq[k * 32 + lane] = central ? (sup ? -r : r) : up;
             const unsigned ball = __ballot_sync(kFull, !central);
             if (!central) tagq[q + __popc(ball & ltMask)] = uint16_t((sup ? 0x8000u : 0u) | (unsigned(k) << 5) | unsigned(lane));
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
                     X += v * (-0.5 * v + g);                   // mcMdlDupire.h:271
                     if (sm.isev[i + 1]) { LogSpotSrc s(X); prd.observe(e, E, s, ctx); ++e; }
                 } else {
-                    X = X * exp(sm.tabA[i] + sm.tabB[i] * g);  // mcMdlBS.h:343
+                    X = X * exp_core(sm.tabA[i] + sm.tabB[i] * g);  // mcMdlBS.h:343 (lean exp: the exponent is a few standard deviations)
                     if (AAD) { histL[size_t(i) * nSlots + slot] = X; histG[size_t(i) * nSlots + slot] = g; }
                     FwdSrc s = bsSample(e, X);
                     prd.observe(e, E, s, ctx); ++e;            // every BS step ends on an event date
@@ -670,15 +670,19 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
                     const double prevFwd = (er > 0 && a.fwd_factors) ? S0 * __ldg(a.fwd_factors + er - 1) : S0;
                     const SampleAdj sa = prd.reverse(er, E, smp, prevFwd);
                     const double ff = a.fwd_factors ? __ldg(a.fwd_factors + er) : 1.0;
-                    Xbar += sa.fwd * ff;
-                    const double abar = valid ? Xbar * S1 : 0.0;           // adjoint of drift_i + std_i g_i
-                    const double ei = exp(sm.tabA[i] + sm.tabB[i] * g);
-                    // dense per-step values: drift, std | numeraire, fwd factor, discount of event er
+                    // Xbar carries the adjoint of log S: S_{i+1} = S_i e_i makes Sbar_i S_i = Sbar_{i+1} S_{i+1}, so the sweep
+                    // needs neither e_i nor a product per step; a sample adds sa.fwd ff S_{i+1}
+                    if (sa.fwd != 0.0) Xbar += sa.fwd * ff * S1;
+                    const double abar = valid ? Xbar : 0.0;                // adjoint of drift_i + std_i g_i
+                    // dense per-step values: drift, std | numeraire, fwd factor, discount, libor of event er (mostly zero: one
+                    // vote decides whether the warp needs their sums at all)
                     double v0 = warp_sum(abar), v1 = warp_sum(abar * g);
-                    double v2 = warp_sum(valid ? sa.num : 0.0), v3 = warp_sum(valid ? sa.fwd * S1 : 0.0);
-                    double v4 = warp_sum(valid ? sa.disc : 0.0), v5 = warp_sum(valid ? sa.lib : 0.0);
+                    double v2 = 0.0, v3 = 0.0, v4 = 0.0, v5 = 0.0;
+                    if (__any_sync(kFull, valid && (sa.num != 0.0 || sa.fwd != 0.0 || sa.disc != 0.0 || sa.lib != 0.0))) {
+                        v2 = warp_sum(valid ? sa.num : 0.0); v3 = warp_sum(valid ? sa.fwd * S1 : 0.0);
+                        v4 = warp_sum(valid ? sa.disc : 0.0); v5 = warp_sum(valid ? sa.lib : 0.0);
+                    }
                     if (lane == 0) { myRow[0] = make_double2(v0, v1); myRow[1] = make_double2(v2, v3); myRow[2] = make_double2(v4, v5); }
-                    Xbar *= ei;
                     X = S0;
                     __syncthreads();
                     if (tid < 6) {
@@ -704,7 +708,7 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
                     FwdSrc smp = bsSample(0, X);
                     const SampleAdj sa = prd.reverse(0, E, smp, 0.0);
                     const double ff = a.fwd_factors ? __ldg(a.fwd_factors) : 1.0;
-                    Xbar += sa.fwd * ff;
+                    Xbar += sa.fwd * ff * X;
                     double v2 = warp_sum(valid ? sa.num : 0.0), v3 = warp_sum(valid ? sa.fwd * X : 0.0);
                     double v4 = warp_sum(valid ? sa.disc : 0.0), v5 = warp_sum(valid ? sa.lib : 0.0);
                     __syncthreads();
@@ -722,7 +726,7 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
             }
             __syncthreads();
             // spot leaf: Dupire L0 = log(S0) -> 1/S0 (mcMdlDupire.h:245); BS: S_0 = spot
-            if (valid) spotBar += kDupire ? Xbar / a.spot : Xbar;
+            if (valid) spotBar += Xbar / a.spot;          // Dupire: L0 = log(S0); Black-Scholes: the adjoint of log S_0, S_0 = spot
         }
     }
 

@@ -216,6 +216,9 @@ int cf_rng_draw(const cf_rng* rng, int dim, uint64_t first_path, uint64_t n_path
  * out[n_paths][dim] uint32 (odd paths repeat their even partner, as the reference caches them) */
 int cf_mrg_numerators(const cf_rng* rng, int dim, uint64_t first_path, uint64_t n_paths, uint32_t* out);
 int cf_inv_normal(const double* p, double* out, uint64_t n);
+/* Device self-test: the number of 32-bit numerators z for which the path kernels' lean quotient z / (m1 + 1)
+ * differs from the IEEE division (must be 0: the uniforms of mrg32k3a are bit-exact) */
+int cf_selftest_mrg_uniform(uint64_t* mismatches);
 
 
 /* Host-buffer runs of a resident plan (same outputs as cf_run_value / cf_run_aad without re-uploading the tables);
@@ -225,14 +228,17 @@ int cf_plan_run_aad(cf_plan* plan, const double* payoff_weights, uint64_t first_
                     double* payoff_sums, double* agg_sum, double* table_adjoints,
                     double* per_path_payoffs, double* per_path_agg);
 int cf_plan_run_aad_multi(cf_plan* plan, uint64_t first_path, uint64_t n_paths, double* payoff_sums, double* risk_tables);
+/* Device time in ms (CUDA events on the launch stream) of the path kernels of the last host-buffer run on the first
+ * device of the context: the dominant kernel of a call made through the host API, for bench accounting. */
+double cf_last_run_kernel_ms(void);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU with one process per GPU.  mcBase.h has no counterpart: its workers share one address space and add
  * their risks in a loop (mcBase.h:737-746, multi: 976-984).  The participants' sum of the result vector -- the
- * path's only exchange step -- is done over peer memory inside the final reduction kernels (cf_comm.cuh), not by a
- * collective call:
+ * path's only exchange step -- is done over peer memory inside the final reduction kernels (cf_comm.cuh: every double
+ * travels as two {half, epoch} words, receivers poll their own memory), not by a collective call:
  *   1. every process: cf_init(1, {its device}); cf_comm_create(world, rank, capacity, handle) allocates its receive
- *      block (2 * world * capacity doubles + flags) and returns a CUDA IPC handle of CF_COMM_HANDLE_BYTES bytes;
+ *      block (2 * world * capacity slots of 16 bytes) and returns a CUDA IPC handle of CF_COMM_HANDLE_BYTES bytes;
  *   2. the launcher gathers the handles in rank order (any transport: torch.distributed, MPI, a file);
  *   3. every process: cf_comm_connect(all handles).
  * From then on every run sums over the participants: cf_run_* / cf_plan_run_* take the WHOLE path range and run this

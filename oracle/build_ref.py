@@ -59,8 +59,13 @@ def patch(name: str, text: str) -> str:
     return text
 
 
-def build(ref: str, force: bool = False, verbose: bool = True) -> str:
+def build(ref: str, force: bool = False, verbose: bool = True, variant: str = "") -> str:
+    """variant "": the checker, -ffp-contract=off.  variant "fma": -ffp-contract=fast into libcfref_fma.so -- the same
+    reference with fused multiply-adds, built only to measure the reference's own sensitivity to the compiler
+    (tests/test_oracle.py: the superbucket chain moves by ~1e-4, prices and AAD risks by ~1e-13)."""
     driver = os.path.join(HERE, "ref_driver.cpp")
+    OUT_SO = os.path.join(OUT_DIR, "libcfref.so" if not variant else f"libcfref_{variant}.so")
+    contract = "-ffp-contract=fast" if variant == "fma" else "-ffp-contract=off"
     if not os.path.isdir(ref):
         if os.path.exists(OUT_SO):
             return OUT_SO
@@ -82,7 +87,7 @@ def build(ref: str, force: bool = False, verbose: bool = True) -> str:
         cmd = [
             # -ffp-contract=off: no fused multiply-adds, like the reference's own /fp:precise x64 build; with
             # contraction on, the finite differences of Dupire's formula (ivs.h:119-138) move by 1e-4 relative
-            "g++", "-std=c++17", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-pthread", "-fPIC", "-shared", "-w",
+            "g++", "-std=c++17", "-O3", "-march=x86-64-v3", contract, "-pthread", "-fPIC", "-shared", "-w",
             # patches 2 and 3: headers MSVC pulls in transitively
             "-include", "cstring", "-include", "functional", "-include", "algorithm",
             "-include", "vector", "-include", "string", "-include", "stdexcept",
@@ -102,3 +107,4 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     a = ap.parse_args()
     print(build(a.ref, a.force))
+    print(build(a.ref, a.force, variant="fma"))

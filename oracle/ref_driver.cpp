@@ -360,4 +360,27 @@ int ref_dupire_superbucket(double spot, double maxDt, const char* productId, con
     });
 }
 
+// dupireSuperbucketBump: main.h:575 (the reference's own finite-difference driver)
+int ref_dupire_superbucket_bump(double spot, double maxDt, const char* productId, const double* notionals,
+                                const double* inclSpots, int nInclSpots, double maxDs, const double* inclTimes,
+                                int nInclTimes, double maxDtVol, const double* strikes, int nStrikes,
+                                const double* mats, int nMats, double vol, double jmpIntens, double jmpAverage,
+                                double jmpStd, int parallel, int useSobol, int numPath, int seed1, int seed2,
+                                double* value_, double* delta, double* vega)
+{
+    return guarded([&] {
+        const Product<double>* prd = getProduct<double>(productId);
+        if (!prd) throw std::runtime_error("ref_dupire_superbucket_bump: product not found");
+        auto r = dupireSuperbucketBump(spot, maxDt, productId, mkNotionals(prd, notionals),
+                                       std::vector<double>(inclSpots, inclSpots + nInclSpots), maxDs,
+                                       std::vector<double>(inclTimes, inclTimes + nInclTimes), maxDtVol,
+                                       std::vector<double>(strikes, strikes + nStrikes),
+                                       std::vector<double>(mats, mats + nMats), vol, jmpIntens, jmpAverage,
+                                       jmpStd, mkNum(parallel, useSobol, numPath, seed1, seed2));
+        *value_ = r.value;
+        *delta = r.delta;
+        std::copy(r.vega.begin(), r.vega.end(), vega);
+    });
+}
+
 }  // extern "C"

@@ -225,7 +225,8 @@ class RefLib:
 
     def dupire_superbucket(self, spot, max_dt, product, notionals, incl_spots, max_ds, incl_times, max_dt_vol,
                            strikes, mats, vol, jmp_intens, jmp_avg, jmp_std, n_path, sobol=True, parallel=True,
-                           seed1=12345, seed2=12346):
+                           seed1=12345, seed2=12346, bump=False):
+        """dupireSuperbucket (main.h:453); bump=True: the reference's finite-difference driver dupireSuperbucketBump (main.h:575)."""
         nots, pn = _d(notionals)
         a, pa = _d(incl_spots)
         b, pb = _d(incl_times)
@@ -233,7 +234,8 @@ class RefLib:
         m, pm = _d(mats)
         vega = np.empty((k.size, m.size))
         v, d = C.c_double(), C.c_double()
-        self._chk(self.lib.ref_dupire_superbucket(
+        fn = self.lib.ref_dupire_superbucket_bump if bump else self.lib.ref_dupire_superbucket
+        self._chk(fn(
             C.c_double(spot), C.c_double(max_dt), product.encode(), pn, pa, C.c_int(a.size), C.c_double(max_ds),
             pb, C.c_int(b.size), C.c_double(max_dt_vol), pk, C.c_int(k.size), pm, C.c_int(m.size),
             C.c_double(vol), C.c_double(jmp_intens), C.c_double(jmp_avg), C.c_double(jmp_std),
@@ -242,11 +244,13 @@ class RefLib:
         return v.value, d.value, vega
 
 
-_singleton = None
+_singletons = {}
 
 
-def get():
-    global _singleton
-    if _singleton is None:
-        _singleton = RefLib()
-    return _singleton
+def get(variant=""):
+    """variant "": the checker (no FMA contraction, like the reference's /fp:precise build); "fma": the same sources
+    compiled with -ffp-contract=fast, used only to measure how much the reference's own results move with the compiler."""
+    if variant not in _singletons:
+        path = SO_PATH if not variant else SO_PATH.replace("libcfref.so", f"libcfref_{variant}.so")
+        _singletons[variant] = RefLib(path)
+    return _singletons[variant]

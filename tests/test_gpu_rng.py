@@ -80,3 +80,12 @@ def test_sequential_rng_interface(cf):
     assert np.max(np.abs(g - R.gaussians(("sobol",), 6, 1000, 1500))) < 1e-14
     u = cf.rng_sequence(False, 3, 0, 5, False, seed1=12345, seed2=12346)
     assert (u == R.mrg32k3a_uniforms(12345, 12346, 3, 0, 5)).all()
+
+
+def test_lean_uniform_quotient_is_the_ieee_quotient_for_every_numerator(eng):
+    """The path kernels compute u = z / (m1 + 1) with a reciprocal + residual correction instead of the IEEE division
+    routine; all 2^32 numerators are compared on the device."""
+    import ctypes as C
+    bad = C.c_uint64(1)
+    eng._chk(eng.lib.cf_selftest_mrg_uniform(C.byref(bad)))
+    assert bad.value == 0

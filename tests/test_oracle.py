@@ -122,3 +122,37 @@ def test_reference_reproduces_survey_pins(ref):
     pv, rv, risks = ref.aad_risk_one("bs0", "eur0", 1 << 16)
     want = [0.5298707170844229, 39.775613482124662, 47.009277343749957, -52.987071708442201]
     assert rel_err(risks, want) < 1e-12
+
+
+def test_the_reference_moves_with_the_compiler(ref):
+    """Pins the noise floor of the superbucket chain (main.h:453-569 through ivs.h:119-138): the same reference sources
+    built with and without fused multiply-adds disagree with each other at the 1e-4 level -- in the calibrated local
+    vols already -- so 1e-8 agreement with "the reference" is not defined for this entry point; prices and AAD risks of
+    the Monte-Carlo path itself move by ~1e-13 only."""
+    from oracle import build_ref, refapi
+    try:
+        build_ref.build("/root/reference", verbose=False, variant="fma")
+        fma = refapi.get("fma")
+    except (FileNotFoundError, OSError):
+        pytest.skip("second reference build not available")
+    fma.start_pool(-1)
+    for r in (ref, fma):
+        r.put_barrier(120.0, 150.0, 1.0, 1.0 / 52, 0.01, False, "uoc_noise")
+    args = dict(spot=100.0, max_dt=0.25, product="uoc_noise", notionals=[1.0, 0.0], incl_spots=[50.0, 100.0, 200.0], max_ds=10.0,
+                incl_times=[0.25, 1.0], max_dt_vol=0.25, strikes=[80.0, 100.0, 120.0, 140.0], mats=[0.5, 1.0], vol=0.15,
+                jmp_intens=0.05, jmp_avg=-0.15, jmp_std=0.10, n_path=1 << 11)
+    va, da, ga = ref.dupire_superbucket(**args)
+    vb, db, gb = fma.dupire_superbucket(**args)
+    spread = np.max(np.abs(ga - gb)) / np.max(np.abs(ga))
+    assert 1e-7 < spread < 1e-2 and 1e-7 < abs(va / vb - 1) < 1e-2
+    la = ref.dupire_calib([50.0, 100.0, 200.0], 10.0, [0.25, 1.0], 0.25, 100.0, 0.15, 0.05, -0.15, 0.10)[2]
+    lb = fma.dupire_calib([50.0, 100.0, 200.0], 10.0, [0.25, 1.0], 0.25, 100.0, 0.15, 0.05, -0.15, 0.10)[2]
+    assert 1e-8 < np.max(np.abs(la - lb)) < 1e-3
+    # the Monte-Carlo path on a fixed model does not have that problem
+    spots = np.arange(55, 201, 5.0); times = np.arange(1, 37) / 12.0
+    vols = 0.15 + 0.10 * np.log(spots[:, None] / 100.0) ** 2 + 0.02 * times[None, :]
+    for r in (ref, fma):
+        r.put_dupire(100.0, spots, times, vols, 0.25, "dup_noise")
+    xa = ref.dupire_aad_risk("dup_noise", "uoc_noise", [1.0, 0.0], 30, 36, 1 << 11)
+    xb = fma.dupire_aad_risk("dup_noise", "uoc_noise", [1.0, 0.0], 30, 36, 1 << 11)
+    assert abs(xa[0] / xb[0] - 1) < 1e-11 and abs(xa[1] / xb[1] - 1) < 1e-9

@@ -11,13 +11,14 @@ OBJ_DIR = os.path.join(LIB_DIR, "obj")
 COMMON = ["cf_device.cuh", "cf_comm.cuh", "cf_kernels.cuh", "cf_pick.h", os.path.join("..", "..", "include", "cf_b200.h")]
 # translation unit -> headers it depends on (besides COMMON); compiled in parallel, relinked when any object changes
 UNITS = {
-    "cf_api.cu": ["cf_tables.h", "cf_dupire.cuh", "cf_dlm.cuh", "cf_multi.cuh"],
+    "cf_api.cu": ["cf_tables.h", "cf_dupire.cuh", "cf_bs.cuh", "cf_dlm.cuh", "cf_multi.cuh"],
     "cf_pick_path.cu": ["cf_multi.cuh"],
     "cf_pick_dlm.cu@4": ["cf_dlm.cuh"],      # one unit per asset-count bucket: -DCF_DLM_AMAX=<n>
     "cf_pick_dlm.cu@8": ["cf_dlm.cuh"],
     "cf_pick_dlm.cu@12": ["cf_dlm.cuh"],
     "cf_pick_dlm.cu@16": ["cf_dlm.cuh"],
     "cf_pick_dupire.cu": ["cf_dupire.cuh"],
+    "cf_pick_bs.cu": ["cf_dupire.cuh", "cf_bs.cuh"],
     "cf_tables.cpp": ["cf_tables.h", "joe_kuo_init.inc"],
 }
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

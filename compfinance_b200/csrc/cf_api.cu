@@ -22,6 +22,7 @@
 #include "cf_dlm.cuh"
 #include "cf_multi.cuh"
 #include "cf_dupire.cuh"
+#include "cf_bs.cuh"
 #include "cf_kernels.cuh"
 #include "cf_tables.h"
 #include "cf_pick.h"
@@ -462,6 +463,9 @@ struct DevPlan {
     DevBuf<uint64_t> mrgJump;
     DevBuf<uint8_t> lut;
     int lutN = 0, storeG = 1;
+    // Black-Scholes fast path (cf_bs.cuh): European / UOC
+    bool bsFast = false;
+    DevBuf<double2> bsDs;
     // Dupire fast kernel (cf_dupire.cuh)
     bool fast = false, hasTimeMap = false;
     int nTimes = 0;
@@ -542,6 +546,7 @@ struct DevPlan {
         if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
         const int nBatches = int(nb64);
         if (mdlKind == CF_MODEL_DISPLACED) { launchDlm(aad, w, first, n, nBatches, dOut, dPerPath, dPerAgg, s, px); return; }
+        if (bsFast) { launchFastBS(aad, w, first, n, dOut, dPerPath, dPerAgg, s, px); return; }
         if (fast && (!aad || hasTimeMap)) { launchFast(aad, w, first, n, dOut, dPerPath, dPerAgg, s, px); return; }
 
         const int grid = std::min(nBatches, 2 * g_sms);
@@ -728,7 +733,7 @@ struct DevPlan {
 
     // The reverse sweep has two forms (cf_dupire.cuh): classic (one path per lane, 8 warps: many live paths per SM) and
     // span (one warp per live path, a lane per S consecutive steps, 16 warps: few live paths per SM, the shard of a
-    // multi-GPU run).  Measured cross-over: about 1300 paths per SM.  CF_DUPIRE_REV = span | classic forces one.
+    // multi-GPU run).  Measured cross-over: about 1100 paths per SM.  CF_DUPIRE_REV = span | classic forces one.
     enum { kRevSpan = 0, kRevClassic = 2 };
     int reverseForm(uint64_t nPad) const
     {
@@ -736,7 +741,7 @@ struct DevPlan {
             const char* e = std::getenv("CF_DUPIRE_REV");
             return !e ? -1 : (std::strcmp(e, "classic") == 0 ? int(kRevClassic) : (std::strcmp(e, "span") == 0 ? int(kRevSpan) : -1));
         }();
-        int form = forced >= 0 ? forced : (nPad <= uint64_t(g_sms) * 1280 ? int(kRevSpan) : int(kRevClassic));
+        int form = forced >= 0 ? forced : (nPad <= uint64_t(g_sms) * 1100 ? int(kRevSpan) : int(kRevClassic));
         // the span kernel's blocks scan the live mask of the whole launch
         if (form == kRevSpan && (spanS == 0 || nPad / 32 > uint64_t(cf::kRevSMaxWords))) form = kRevClassic;
         return form;
@@ -754,6 +759,80 @@ struct DevPlan {
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
         CF_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    }
+
+    // Black-Scholes x {European, UOC}: the shared forward kernel with the log-normal step, the span reverse of cf_bs.cuh
+    // over the live paths, one reduction (with the rank sum).  Launches of at most 2^21 paths (history: n_steps x 8 bytes
+    // per path).
+    void launchFastBS(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut,
+                      double* dPerPath, double* dPerAgg, cudaStream_t s, const cf::DPeers* px)
+    {
+        static const bool pdl = [] { const char* e = std::getenv("CF_PDL"); return !e || std::atoi(e) != 0; }();
+        constexpr uint64_t kChunkBS = kFastChunk;
+        const bool sob = rngKind == CF_RNG_SOBOL;
+        const uint64_t maxChunk = std::min<uint64_t>(n, kChunkBS);
+        const int fwdP = forwardP(maxChunk), fwdWarps = cf::kFwdWarps;
+        const uint64_t quantum = 256ull * fwdP;
+        const int histRow = (D + 3) / 4 * 4;
+        const uint64_t maxPad = (maxChunk + quantum - 1) / quantum * quantum;
+        const int gridF = std::min(int(maxPad / quantum) * 8, g_sms);
+        const int minGridR = int((maxPad / 32 + cf::kBsMaxWords - 1) / cf::kBsMaxWords);
+        const int gridR = std::max(int(std::min<uint64_t>(maxPad / 32, uint64_t(g_sms))), minGridR);
+        const int nAdjBs = cf::bs_adj_size(D, E);
+        scratch.need(scratch.partial, size_t(gridF) * (size_t(nPay) + 1), s);
+        if (aad) {
+            scratch.need(scratch.hist, size_t(histRow) * maxPad, s);
+            scratch.need(scratch.state, 2 * maxPad, s);
+            scratch.need(scratch.live, size_t(maxPad / 32), s);
+            scratch.need(scratch.partialRev, size_t(gridR) * nAdjBs, s);
+        }
+        DKernel fwd = cf::pick_bs_forward(prdKind, aad, rngKind, fwdP);
+        const size_t smemF = fwdP == 2 ? cf::dupire_smem_fwd4<2, cf::kFwdChunk>(D, 0, dim, sob, 0, fwdWarps, true).total
+                                       : cf::dupire_smem_fwd4<1, cf::kFwdChunk1>(D, 0, dim, sob, 0, fwdWarps, true).total;
+        const int S = cf::dupire_span_steps(D);
+        DKernel rev = aad ? cf::pick_bs_reverse(prdKind, S) : nullptr;
+        const size_t smemR = cf::bs_smem_rev(D, E).total;
+        CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fwd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
+        if (aad) CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(rev), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemR)));
+        auto ev = takeEvents();
+        CF_CUDA(cudaEventRecord(ev.first, s));
+        for (uint64_t off = 0; off < n; off += kChunkBS) {
+            const uint64_t cnt = std::min<uint64_t>(kChunkBS, n - off);
+            cf::DArgs a = dbase;
+            a.first_path = first + off; a.n_paths = cnt;
+            a.n_pad = (cnt + quantum - 1) / quantum * quantum;
+            a.accumulate = off ? 1 : 0;
+            a.w[0] = a.w[1] = 0.0;
+            if (aad) for (int k = 0; k < nPay && k < cf::kMaxPay; ++k) a.w[k] = w[k];
+            a.partial = scratch.partial.p; a.partial_rev = scratch.partialRev.p;
+            a.hist = scratch.hist.p; a.state = scratch.state.p; a.live = scratch.live.p;
+            a.per_path_payoffs = dPerPath ? dPerPath + off * nPay : nullptr;
+            a.per_path_agg = dPerAgg ? dPerAgg + off : nullptr;
+            a.n_units = int(a.n_pad / quantum) * 8;
+            launchKernel(fwd, gridF, fwdWarps * 32, smemF, s, a, false);
+            ++g_launches;
+            if (aad) {
+                launchKernel(rev, gridR, cf::kBsRevBlock, smemR, s, a, pdl);
+                ++g_launches;
+            }
+        }
+        CF_CUDA(cudaEventRecord(ev.second, s));
+        events.push_back(ev);
+        const int nHead = aad ? nPay + 1 : nPay, nTail = aad ? nAdjBs : 0, nOut = nHead + nTail;
+        cf::DPeers pr{};
+        if (px) {
+            if (size_t(nOut) > px->cap) throw CfError("cf_b200: result vector longer than the communicator's capacity");
+            pr = *px;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(unsigned((nOut * 32 + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = (pdl && aad) ? 1 : 0;
+        const double* cHead = scratch.partial.p; const double* cTail = scratch.partialRev.p;
+        CF_CUDA(cudaLaunchKernelEx(&cfg, cf::rows_reduce_kernel, cHead, gridF, nPay + 1, nHead, cTail, gridR, nAdjBs, nTail, dOut, pr));
+        ++g_launches;
     }
 
     void launchFast(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut,
@@ -1127,6 +1206,56 @@ std::unique_ptr<DevPlan> make_plan(const cf_model* mdl, const cf_product* prd, c
                 d.n_payoffs = prd->n_payoffs; d.is_put = prd->is_put;
                 d.strike = prd->strike; d.barrier = prd->barrier; d.smooth = prd->smooth;
             }
+        }
+    }
+    if (mdl->kind == CF_MODEL_BS && (prd->kind == CF_PRODUCT_EUROPEAN || prd->kind == CF_PRODUCT_UOC)) {
+        // fast path (cf_bs.cuh): log-normal steps in log space.  The barrier is monitored on the forward of every sample;
+        // the fast kernels monitor the spot, so every forward factor must be 1 (the UOC of mcPrd.h asks for the forward
+        // to the sample date itself); the payoff date may carry a forward factor, a discount and a numeraire
+        const int D = p->D, E = p->E;
+        bool ok = cf::dupire_span_steps(D) > 0 && mdl->spot > 0.0
+                  && cf::dupire_smem_fwd4<2, cf::kFwdChunk>(D, 0, p->dim, rng->kind == CF_RNG_SOBOL, 0, cf::kFwdWarps, true).total <= kFastSmemLimit
+                  && cf::dupire_smem_fwd4<1, cf::kFwdChunk1>(D, 0, p->dim, rng->kind == CF_RNG_SOBOL, 0, cf::kFwdWarps, true).total <= kFastSmemLimit
+                  && cf::bs_smem_rev(D, E).total <= kFastSmemLimit;
+        if (prd->kind == CF_PRODUCT_UOC && mdl->fwd_factors)
+            for (int e = 0; e < E; ++e) ok = ok && mdl->fwd_factors[e] == 1.0;
+        for (int i = 0; i < D; ++i) ok = ok && mdl->bs_stds[i] > 1.0e-12;      // g_i is recovered from the log-spots by a division
+        const double numT = mdl->numeraires ? mdl->numeraires[E - 1] : 1.0, ffT = mdl->fwd_factors ? mdl->fwd_factors[E - 1] : 1.0;
+        const double discT = mdl->discounts ? mdl->discounts[E - 1] : 1.0;
+        ok = ok && numT > 0.0 && ffT > 0.0 && discT > 0.0;
+        static const bool off = [] { const char* e = std::getenv("CF_BS_FAST"); return e && std::atoi(e) == 0; }();
+        if (ok && !off) {
+            std::vector<double2> ds(static_cast<size_t>(D));
+            for (int i = 0; i < D; ++i) ds[size_t(i)] = make_double2(mdl->bs_drifts[i], mdl->bs_stds[i]);
+            p->bsDs.upload(ds.data(), ds.size());
+            const int nWords = (D + 31) / 32;
+            std::vector<uint32_t> bits(size_t(nWords), 0u);
+            for (int i = 0; i + 1 < D; ++i)
+                if (mdl->is_event[i + 1]) bits[size_t(i >> 5)] |= 1u << (i & 31);
+            p->stepBits.upload(bits.data(), bits.size());
+            cf::DArgs& d = p->dbase;
+            d.seed1 = rng->seed1; d.seed2 = rng->seed2; d.dim = p->dim;
+            d.sobol_dir = p->sobolDir.p; d.mrg_jump = p->mrgJump.p;
+            d.n_steps = D; d.n_knots = 0; d.n_cells = 0; d.n_events = E;
+            d.ev_bits = p->stepBits.p; d.ev0 = mdl->is_event[0] ? 1 : 0;
+            d.spot = mdl->spot; d.shift = 0.0;
+            d.bs_ds = p->bsDs.p; d.fwd_factor = ffT; d.bs_num = numT; d.bs_disc = discT;
+            d.pay_scale = prd->kind == CF_PRODUCT_EUROPEAN ? discT / numT : 1.0 / numT;
+            d.n_payoffs = prd->n_payoffs; d.is_put = prd->is_put;
+            d.strike = prd->strike; d.barrier = prd->barrier; d.smooth = prd->smooth;
+            const bool sob = rng->kind == CF_RNG_SOBOL;
+            auto central = [sob](uint32_t zz) {
+                volatile double u = sob ? CF_ONEOVER2POW32 * double(zz) : double(zz) / 4294967088.0;
+                volatile double xx = u - 0.5;
+                return std::fabs(xx) < 0.42;
+            };
+            uint32_t lo = 0u, hi = 0x80000000u;
+            while (hi - lo > 1u) { const uint32_t mid = lo + (hi - lo) / 2u; if (central(mid)) hi = mid; else lo = mid; }
+            const uint32_t firstC = hi;
+            lo = 0x80000000u; hi = 0xffffffffu;
+            while (hi - lo > 1u) { const uint32_t mid = lo + (hi - lo) / 2u; if (central(mid)) lo = mid; else hi = mid; }
+            d.tail_lo = firstC; d.tail_span = lo - firstC;
+            p->bsFast = true;
         }
     }
     a.n_payoffs = prd->n_payoffs; a.is_put = prd->is_put;

@@ -21,6 +21,9 @@ LKernel pick_dlm_kernel(int n_assets, int prd, bool aad, int rng);
 DKernel pick_dupire_forward(int prd, bool aad, int rng, int fwdP, int chunk);
 DKernel pick_dupire_reverse(int prd);
 int dupire_span_steps(int n_steps);             // steps per lane of the span reverse kernel for this timeline, 0: none
-DKernel pick_dupire_reverse_span(int prd, int S);   // one warp per live path, S steps per lane      // four lanes per live path (small shards)
+DKernel pick_dupire_reverse_span(int prd, int S);
+// cf_pick_bs.cu: Black-Scholes x {European, UOC} fast path (fwdP = 1: 8-step chunks, 2: 4-step chunks)
+DKernel pick_bs_forward(int prd, bool aad, int rng, int fwdP);
+DKernel pick_bs_reverse(int prd, int S);   // one warp per live path, S steps per lane      // four lanes per live path (small shards)
 
 }  // namespace cf

@@ -7,8 +7,8 @@ namespace {
 template <int PRD, int P, int NW, int CH>
 DKernel pickF(bool aad, int rng)
 {
-    if (aad) return rng == CF_RNG_SOBOL ? dupire_forward4_kernel<PRD, true, CF_RNG_SOBOL, P, NW, CH> : dupire_forward4_kernel<PRD, true, CF_RNG_MRG32K3A, P, NW, CH>;
-    return rng == CF_RNG_SOBOL ? dupire_forward4_kernel<PRD, false, CF_RNG_SOBOL, P, NW, CH> : dupire_forward4_kernel<PRD, false, CF_RNG_MRG32K3A, P, NW, CH>;
+    if (aad) return rng == CF_RNG_SOBOL ? dupire_forward4_kernel<CF_MODEL_DUPIRE, PRD, true, CF_RNG_SOBOL, P, NW, CH> : dupire_forward4_kernel<CF_MODEL_DUPIRE, PRD, true, CF_RNG_MRG32K3A, P, NW, CH>;
+    return rng == CF_RNG_SOBOL ? dupire_forward4_kernel<CF_MODEL_DUPIRE, PRD, false, CF_RNG_SOBOL, P, NW, CH> : dupire_forward4_kernel<CF_MODEL_DUPIRE, PRD, false, CF_RNG_MRG32K3A, P, NW, CH>;
 }
 }  // namespace
 

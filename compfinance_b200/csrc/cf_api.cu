@@ -545,7 +545,7 @@ struct DevPlan {
         const uint64_t nb64 = (n + cf::kBlock - 1) / cf::kBlock;
         if (nb64 > 0x7fffffffull) throw CfError("cf_b200: too many paths in one launch");
         const int nBatches = int(nb64);
-        if (mdlKind == CF_MODEL_DISPLACED) { launchDlm(aad, w, first, n, nBatches, dOut, dPerPath, dPerAgg, s, px); return; }
+        if (mdlKind == CF_MODEL_DISPLACED) { launchDlm(aad, w, first, n, dOut, dPerPath, dPerAgg, s, px); return; }
         if (bsFast) { launchFastBS(aad, w, first, n, dOut, dPerPath, dPerAgg, s, px); return; }
         if (fast && (!aad || hasTimeMap)) { launchFast(aad, w, first, n, dOut, dPerPath, dPerAgg, s, px); return; }
 
@@ -602,17 +602,38 @@ struct DevPlan {
 
     using LKernel = cf::LKernel;
 
-    void launchDlm(bool aad, const double* w, uint64_t first, uint64_t n, int nBatches, double* dOut, double* dPerPath,
+
+    void launchDlm(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut, double* dPerPath,
                    double* dPerAgg, cudaStream_t s, const cf::DPeers* px)
     {
-        const int grid = std::min(nBatches, 2 * g_sms);
+        // one block per SM: 12 warps with mrg32k3a when their scratch rows fit in shared memory, else 8
+        const bool sobol = rngKind == CF_RNG_SOBOL;
+        const int amax = cf::dlm_bucket(A);
+        int warps = 0, stepsInSmem = 0;
+        size_t smem = 0;
+        for (int tryWarps : {12, 8}) {
+            if (sobol && tryWarps != 8) continue;
+            for (int trySteps : {1, 0}) {
+                if (warps || (trySteps && !cf::dlm_steps_fit(A, D))) continue;
+                smem = cf::dlm_smem(A, amax, D, E, nPay, dim, sobol, aad, tryWarps, lbase.has_alpha != 0, trySteps != 0).total;
+                if (smem <= kFastSmemLimit) { warps = tryWarps; stepsInSmem = trySteps; }
+            }
+        }
+        if (!warps) throw CfError("cf_b200: displaced model tables do not fit in shared memory (n_steps * n_assets or payoffs too large)");
+        const int threads = warps * 32;
+        const int nBatchesL = int((n + uint64_t(threads) - 1) / uint64_t(threads));
+        const int grid = std::min(nBatchesL, g_sms);
         const size_t stride = aad ? size_t(nPay) + 1 + nAdj : size_t(nPay);
         partialStride = int(stride);
         scratch.need(scratch.partial, size_t(grid) * stride, s);
-        if (aad) scratch.need(scratch.hist, size_t(D) * (2 * A + 1) * size_t(grid) * cf::kBlock, s);
         cf::LArgs a = lbase;
-        a.first_path = first; a.n_paths = n; a.n_batches = nBatches;
+        a.first_path = first; a.n_paths = n; a.n_batches = nBatchesL; a.steps_in_smem = stepsInSmem;
         if (aad) {
+            scratch.need(scratch.hist, size_t(D) * (2 * A + 1) * size_t(grid) * threads, s);
+            const size_t tabDoubles = size_t(grid) * warps * size_t(cf::dlm_warp_tab(A, D, E));
+            scratch.need(scratch.tmp, tabDoubles, s);
+            CF_CUDA(cudaMemsetAsync(scratch.tmp.p, 0, sizeof(double) * tabDoubles, s));
+            a.warp_tab = scratch.tmp.p;
             // the weights are read by the kernel from device memory: stage them on the launch stream
             CF_CUDA(cudaMemcpyAsync(lW.p, w, sizeof(double) * size_t(nPay), cudaMemcpyHostToDevice, s));
             CF_CUDA(cudaStreamSynchronize(s));
@@ -620,14 +641,12 @@ struct DevPlan {
         a.w = lW.p;
         a.partial = scratch.partial.p; a.partial_stride = partialStride;
         a.per_path_payoffs = dPerPath; a.per_path_agg = dPerAgg; a.hist = scratch.hist.p;
-        LKernel fn = cf::pick_dlm_kernel(A, prdKind, aad, rngKind);
+        LKernel fn = cf::pick_dlm_kernel(A, prdKind, aad, rngKind, warps);
         if (!fn) throw CfError("cf_b200: MultiStats is a value-only test instrument on the device (no AAD)");
-        const size_t smem = cf::dlm_smem(A, D, E, nPay, dim, rngKind == CF_RNG_SOBOL, aad).total;
-        if (smem > kFastSmemLimit) throw CfError("cf_b200: displaced model tables do not fit in shared memory (n_steps * n_assets or payoffs too large)");
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         auto ev = takeEvents();
         CF_CUDA(cudaEventRecord(ev.first, s));
-        fn<<<grid, cf::kBlock, smem, s>>>(a);
+        fn<<<grid, threads, smem, s>>>(a);
         CF_CUDA(cudaEventRecord(ev.second, s));
         events.push_back(ev);
         CF_CUDA(cudaGetLastError());
@@ -995,6 +1014,9 @@ std::unique_ptr<DevPlan> make_plan(const cf_model* mdl, const cf_product* prd, c
         l.n_payoffs = prd->n_payoffs; l.n_strikes = prd->kind == CF_PRODUCT_BASKETS ? prd->n_payoffs : 0;
         l.strike = prd->strike; l.ko = prd->barrier; l.smooth = prd->smooth; l.coupon = prd->coupon;
         l.cpn_dt = prd->event_dt ? prd->event_dt[0] : 0.0;
+        l.has_alpha = 0;
+        for (int k = 0; k < p->A; ++k) if (mdl->dlm_dynamics[k] >= 2) l.has_alpha = 1;
+
         l.strikes = p->lStrikes.p; l.pweights = p->lPw.p;
     }
     if (prd->kind == CF_PRODUCT_EUROPEANS) {

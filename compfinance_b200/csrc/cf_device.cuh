@@ -141,9 +141,17 @@ struct MrgThread {
     __device__ __forceinline__ void init(uint32_t seedA, uint32_t seedB, uint64_t pairIndex,
                                          const uint64_t* __restrict__ jump)
     {
-        uint64_t X[3] = {seedA, seedA, seedA}, Y[3] = {seedB, seedB, seedB};
-        for (int k = 0; k < 64 && (pairIndex >> k); ++k) {
-            if (!((pairIndex >> k) & 1ull)) continue;
+        x0 = x1 = x2 = seedA;
+        y0 = y1 = y2 = seedB;
+        advance(pairIndex, jump);
+    }
+
+    // moves the state `count` path pairs (count * D numbers) down the stream: one jump matrix per set bit of count
+    __device__ __forceinline__ void advance(uint64_t count, const uint64_t* __restrict__ jump)
+    {
+        uint64_t X[3] = {x0, x1, x2}, Y[3] = {y0, y1, y2};
+        for (int k = 0; k < 64 && (count >> k); ++k) {
+            if (!((count >> k) & 1ull)) continue;
             const uint64_t* M1 = jump + (k * 2 + 0) * 9;
             const uint64_t* M2 = jump + (k * 2 + 1) * 9;
             uint64_t nx[3], ny[3];

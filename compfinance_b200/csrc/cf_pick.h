@@ -15,7 +15,9 @@ KernelFn pick_path_kernel(int mdl, int prd, bool aad, int rng);
 // cf_pick_path.cu: itemised risk of Dupire x Europeans
 MKernel pick_multi_kernel(int rng);
 // cf_pick_dlm.cu: displaced multi-asset model, instantiated for up to 4 / 8 / 12 / 16 assets; nullptr: MultiStats with AAD
-LKernel pick_dlm_kernel(int n_assets, int prd, bool aad, int rng);
+// warps: 8 (Sobol, or when the rows of 12 warps do not fit in shared memory) or 12 (mrg32k3a)
+LKernel pick_dlm_kernel(int n_assets, int prd, bool aad, int rng, int warps);
+inline int dlm_bucket(int n_assets) { return n_assets <= 4 ? 4 : n_assets <= 8 ? 8 : n_assets <= 12 ? 12 : 16; }
 // cf_pick_dupire.cu: the north-star kernels; fwdP = paths per thread of the forward kernel, 1 or 2 (kFwdWarps warps per block),
 // chunk = steps of Gaussians per fill (kFwdChunk; kFwdChunk1 is also built for fwdP = 1)
 DKernel pick_dupire_forward(int prd, bool aad, int rng, int fwdP, int chunk);

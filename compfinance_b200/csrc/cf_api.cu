@@ -267,7 +267,7 @@ struct UploadScope {
 // stream (stream-ordered allocation: a buffer is only released after the work queued before it on that stream), never
 // shrunk.  A plan is used on one stream at a time; two plans never share scratch.
 struct Scratch {
-    DevBuf<double> hist, state, partial, partialRev, wtab, btab, tmp, local;
+    DevBuf<double> hist, state, partial, partialRev, wtab, btab, tmp, local, local2;
     DevBuf<uint32_t> live;
     template <class T> void need(DevBuf<T>& b, size_t n, cudaStream_t s) { if (b.n < n) b.alloc(n, s); }
 };
@@ -485,7 +485,7 @@ struct DevPlan {
     cf::LArgs lbase{};
     DevBuf<double> eStrikes;
     DevBuf<int32_t> eOff;
-    DevBuf<double> lSpots, lChol, lAlphas, lDynFwd, lDrifts, lStds, lFf, lNum, lStrikes, lPw, lW;
+    DevBuf<double> lSpots, lChol, lAlphas, lDynFwd, lDrifts, lStds, lStepPack, lFf, lNum, lStrikes, lPw, lW;
     DevBuf<int32_t> lDyn;
     int A = 1;
     int partialStride = 0;
@@ -606,13 +606,14 @@ struct DevPlan {
     void launchDlm(bool aad, const double* w, uint64_t first, uint64_t n, double* dOut, double* dPerPath,
                    double* dPerAgg, cudaStream_t s, const cf::DPeers* px)
     {
-        // one block per SM: 12 warps with mrg32k3a when their scratch rows fit in shared memory, else 8
+        // one block per SM of 8 warps (255 registers); CF_DLM_WARPS=12 tries 12 warps with mrg32k3a (168 registers: measured slower)
         const bool sobol = rngKind == CF_RNG_SOBOL;
         const int amax = cf::dlm_bucket(A);
         int warps = 0, stepsInSmem = 0;
         size_t smem = 0;
+        static const int forcedWarps = [] { const char* e = std::getenv("CF_DLM_WARPS"); return e ? std::atoi(e) : 0; }();
         for (int tryWarps : {12, 8}) {
-            if (sobol && tryWarps != 8) continue;
+            if ((sobol || forcedWarps != 12) && tryWarps != 8) continue;        // 8 warps measured faster than 12 (registers)
             for (int trySteps : {1, 0}) {
                 if (warps || (trySteps && !cf::dlm_steps_fit(A, D))) continue;
                 smem = cf::dlm_smem(A, amax, D, E, nPay, dim, sobol, aad, tryWarps, lbase.has_alpha != 0, trySteps != 0).total;
@@ -634,6 +635,12 @@ struct DevPlan {
             scratch.need(scratch.tmp, tabDoubles, s);
             CF_CUDA(cudaMemsetAsync(scratch.tmp.p, 0, sizeof(double) * tabDoubles, s));
             a.warp_tab = scratch.tmp.p;
+            if (lbase.has_alpha) {
+                const size_t cols = size_t(A) * size_t(grid) * threads;
+                scratch.need(scratch.local2, cols, s);
+                CF_CUDA(cudaMemsetAsync(scratch.local2.p, 0, sizeof(double) * cols, s));
+                a.alpha_cols = scratch.local2.p;
+            }
             // the weights are read by the kernel from device memory: stage them on the launch stream
             CF_CUDA(cudaMemcpyAsync(lW.p, w, sizeof(double) * size_t(nPay), cudaMemcpyHostToDevice, s));
             CF_CUDA(cudaStreamSynchronize(s));
@@ -967,6 +974,11 @@ std::unique_ptr<DevPlan> make_plan(const cf_model* mdl, const cf_product* prd, c
         p->lDyn.upload(mdl->dlm_dynamics, A);
         p->lDynFwd.upload(mdl->dlm_dyn_fwd, D * A); p->lDrifts.upload(mdl->dlm_drifts, D * A); p->lStds.upload(mdl->dlm_stds, D * A);
         p->lFf.upload(mdl->dlm_fwd_factors, E * A);
+        {
+            std::vector<double> pack(4 * (D * A + 4), 0.0);        // four spare entries: the kernel steps assets in groups of four
+            for (size_t i = 0; i < D * A; ++i) { pack[4 * i] = mdl->dlm_dyn_fwd[i]; pack[4 * i + 1] = mdl->dlm_drifts[i]; pack[4 * i + 2] = mdl->dlm_stds[i]; }
+            p->lStepPack.upload(pack.data(), pack.size());
+        }
         if (mdl->numeraires) p->lNum.upload(mdl->numeraires, E);
         if (prd->strikes && prd->kind == CF_PRODUCT_BASKETS) p->lStrikes.upload(prd->strikes, size_t(prd->n_payoffs));
         if (prd->weights) p->lPw.upload(prd->weights, A);
@@ -1010,6 +1022,7 @@ std::unique_ptr<DevPlan> make_plan(const cf_model* mdl, const cf_product* prd, c
         l.spots = p->lSpots.p; l.chol = p->lChol.p; l.alphas = p->lAlphas.p; l.dyn = p->lDyn.p;
         for (int k = 0; k < p->A; ++k)
             for (int j = 0; j <= k; ++j) l.cholv[k * (k + 1) / 2 + j] = mdl->dlm_chol[size_t(k) * p->A + j];
+        l.step_pack = reinterpret_cast<const double4*>(p->lStepPack.p);
         l.dynFwd = p->lDynFwd.p; l.drifts = p->lDrifts.p; l.stds = p->lStds.p; l.ff = p->lFf.p; l.num = p->lNum.p;
         l.n_payoffs = prd->n_payoffs; l.n_strikes = prd->kind == CF_PRODUCT_BASKETS ? prd->n_payoffs : 0;
         l.strike = prd->strike; l.ko = prd->barrier; l.smooth = prd->smooth; l.coupon = prd->coupon;

@@ -51,6 +51,7 @@ struct LArgs {
     const double*  num;            // [E] or null (numeraire not requested: Sample default 1)
     int      has_alpha;            // some asset is sur- or subnormal
     int      steps_in_smem;        // the [D][A] step tables fit in shared memory
+    const double4* step_pack;      // [D][A]: (dynFwd, drift, std, -), the three step tables side by side
     // product
     int      n_payoffs, n_strikes;
     double   strike, ko, smooth, coupon, cpn_dt;
@@ -64,6 +65,7 @@ struct LArgs {
     double*  per_path_agg;
     double*  hist;                 // [D][2 A + 1][grid * NW * 32]
     double*  warp_tab;             // [grid * NW][dlm_step_tables + A], zeroed before the launch (AAD)
+    double*  alpha_cols;           // [A][grid * NW * 32], zeroed before the launch (AAD with sur- / subnormal assets)
 };
 
 // Layout of the table-adjoint vector of the displaced model (after the aggregate):
@@ -86,14 +88,14 @@ __host__ __device__ inline LSmemSizes dlm_smem(int A, int AMAX, int D, int E, in
     LSmemSizes s{};
     s.pay = align16(sizeof(double) * nWarps * size_t(nPay));
     s.red = align16(sizeof(double) * nWarps);
-    s.evc = align16(sizeof(double) * size_t(E) * A);
+    s.evc = align16(sizeof(double) * (size_t(E) * A + 4));
     s.inum = align16(sizeof(double) * size_t(E));
-    s.asset = sizeof(double) * 4 * size_t(A);
-    s.steps = stepsInSmem ? sizeof(double) * 4 * size_t(D) * A : 0;
+    s.asset = sizeof(double) * 4 * size_t(AMAX);
+    s.steps = stepsInSmem ? sizeof(double) * 4 * (size_t(D) * A + 4) : 0;            // groups of four assets read past the last one
     s.logt = sizeof(double) * 2 * 128;
     s.dirlow = sobol ? align16(sizeof(uint32_t) * size_t(dim) * kLowBits) : 0;
     s.base = sobol ? align16(sizeof(uint32_t) * 2 * size_t(dim)) : 0;
-    s.alpha = (aad && hasAlpha) ? sizeof(double) * size_t(A) * nWarps * 32 : 0;
+    s.alpha = 0;
     s.gq = sizeof(double) * size_t(AMAX) * 32;                                            // forward: the warp's Gaussians of a step,
     const size_t fwd = s.gq + sizeof(uint16_t) * size_t(AMAX) * 32;                       //   then its tail tags
     const size_t scr = aad ? sizeof(double) * size_t(dlm_rows(A, AMAX)) * kDlmRow : 0;          // reverse: the warp's rows (same memory)
@@ -162,6 +164,12 @@ __device__ __forceinline__ double dlm_row_sum(const double* row)
     return (s0 + s1) + (s2 + s3);
 }
 
+// fire-and-forget addition in L2: no result, no scoreboard
+__device__ __forceinline__ void dlm_red(double* addr, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;" :: "l"(addr), "d"(v) : "memory");
+}
+
 // Rounds of 32 (k, j <= k) pairs of the Cholesky adjoint owned by a lane
 template <int AMAX> struct DlmPairs { static constexpr int kRounds = (AMAX * (AMAX + 1) / 2 + 31) / 32; };
 
@@ -191,7 +199,6 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
     double2* logT = reinterpret_cast<double2*>(p);      p += z.logt;
     uint32_t* dirlow = reinterpret_cast<uint32_t*>(p);  p += z.dirlow;
     uint32_t* base = reinterpret_cast<uint32_t*>(p);    p += z.base;
-    double* alphaCol = reinterpret_cast<double*>(p);    p += z.alpha;     // [A][kT], a column per thread
     double* work = reinterpret_cast<double*>(p) + size_t(warp) * (z.work / NW / sizeof(double));
     double* gq = work;                                                    // forward: [AMAX][32]
     double* scr = work;                                                   // reverse: [6 A + 1][34]
@@ -200,40 +207,52 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
     const int nStepTab = dlm_step_tables(A, D, E);
     const int oFwd = 0, oDrift = D * A, oStd = 2 * D * A, oNum = 3 * D * A, oFf = 3 * D * A + E, oSpot = nStepTab;
     for (int i = tid; i < NW * nPay; i += kT) payRows[i] = 0.0;
-    for (int i = tid; i < E * A; i += kT) {
-        const double f = __ldg(a.ff + i);
-        evC[i] = kAuto ? f / __ldg(a.pweights + (i % A)) : f;
+    for (int i = tid; i < E * A + 4; i += kT) {
+        const double f = i < E * A ? __ldg(a.ff + i) : 0.0;
+        evC[i] = (kAuto && i < E * A) ? f / __ldg(a.pweights + (i % A)) : f;
     }
     for (int i = tid; i < E; i += kT) invNum[i] = a.num ? 1.0 / __ldg(a.num + i) : 1.0;
-    for (int i = tid; i < A; i += kT) {
-        const int dyn = __ldg(a.dyn + i);
-        const double al = __ldg(a.alphas + i);
-        assetC[i] = make_double4(dyn == 2 ? al : dyn == 3 ? -al : 0.0, double(dyn), kAuto ? 1.0 / __ldg(a.pweights + i) : 0.0, al);
+    for (int i = tid; i < AMAX; i += kT) {
+        const int dyn = i < A ? __ldg(a.dyn + i) : 0;
+        const double al = i < A ? __ldg(a.alphas + i) : 0.0;
+        assetC[i] = make_double4(dyn == 2 ? al : dyn == 3 ? -al : 0.0, double(dyn), (kAuto && i < A) ? 1.0 / __ldg(a.pweights + i) : 0.0, al);
     }
     if (stepsInSmem)
-        for (int i = tid; i < D * A; i += kT) stepS[i] = make_double4(__ldg(a.dynFwd + i), __ldg(a.drifts + i), __ldg(a.stds + i), 0.0);
+        for (int i = tid; i < D * A + 4; i += kT) stepS[i] = a.step_pack[i];          // the pack carries four spare entries
     for (int i = tid; i < 128; i += kT) {
         const double c0 = 1.0 / (1.0 + (double(i) + 0.5) * (1.0 / 128.0));
         const double c = __hiloint2double(__double2hiint(c0) & 0xfffffc00, 0);
         logT[i] = make_double2(c, -log(c));
     }
-    if (AAD && hasAlpha) for (int i = tid; i < A * kT; i += kT) alphaCol[i] = 0.0;
     if (kSobol) sobol_load_low(dirlow, a.sobol_dir, a.dim);
     __syncthreads();
     double* myPay = payRows + size_t(warp) * nPay;
     double* myTab = AAD ? a.warp_tab + (size_t(blockIdx.x) * NW + warp) * size_t(dlm_warp_tab(A, D, E)) : nullptr;
 
-    auto stepConst = [&](int idx) -> double4 {
-        if (stepsInSmem) return stepS[idx];
-        return make_double4(__ldg(a.dynFwd + idx), __ldg(a.drifts + idx), __ldg(a.stds + idx), 0.0);
-    };
+    const double4* stepP = stepsInSmem ? stepS : a.step_pack;      // shared or global, one code path
+    auto stepConst = [&](int idx) -> double4 { return stepP[idx]; };
 
     SobolThread sob;
     MrgThread mrg, mrgStart;
+    // antithetic partners: lane 2 j steps the first component of the pair's generator, lane 2 j + 1 the second
+    uint32_t hs0 = 0, hs1 = 0, hs2 = 0;
     const unsigned ltMask = (1u << lane) - 1u;
     // antithetic partners in adjacent lanes share the conversion work
     const bool share = !kSobol && ((a.first_path & 1ull) == 0);
     const int parity = lane & 1;
+    const uint32_t hC1 = parity ? 527612u : 1403580u, hC2 = parity ? 1370589u : 810728u;
+    const uint32_t hM = parity ? uint32_t(kM2) : uint32_t(kM1), hFold = parity ? 22853u : 209u;
+    // one number of the pair's stream (mrg32k3a.h:55-81): own component here, the partner's by shuffle
+    auto nextShared = [&]() -> uint32_t {
+        const uint64_t pr = uint64_t(hC1) * (parity ? hs0 : hs1) + uint64_t(hC2) * uint64_t(hM - hs2);     // < 2^54
+        uint64_t t = uint64_t(uint32_t(pr)) + uint64_t(uint32_t(pr >> 32)) * hFold;                        // < 2^38
+        t = uint64_t(uint32_t(t)) + uint64_t(uint32_t(t >> 32) * hFold);                                   // < 2^32 + 2^21
+        const uint32_t v = uint32_t(t >= hM ? t - hM : t);
+        hs2 = hs1; hs1 = hs0; hs0 = v;
+        const uint32_t o = __shfl_xor_sync(kFull, v, 1);
+        const uint32_t x = parity ? o : v, y = parity ? v : o;
+        return x > y ? x - y : uint32_t(uint64_t(x) + kM1 - y);
+    };
 
     // the Gaussian of one number of the stream, or its tail marker: central branch of invNormalCdf (gaussians.h:73-78)
     // inline, tail (80-86) parked.  Returns true when central.
@@ -257,9 +276,9 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
         __syncwarp();
         if (share) {
             for (int k0 = 0; k0 < A; k0 += 2) {
-                const uint32_t z0 = mrg.next();
+                const uint32_t z0 = nextShared();
                 uint32_t z1 = z0;
-                if (k0 + 1 < A) z1 = mrg.next();
+                if (k0 + 1 < A) z1 = nextShared();
                 const int k = k0 + parity;
                 double val; bool sup;
                 const bool central = convert(parity ? z1 : z0, val, sup) || k >= A;
@@ -320,6 +339,20 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
             cholAcc[q] = 0.0;
         }
     }
+    // table entry of row r = lane + 32 q of the step's rows: base + A * event (forward factors), + event (numeraire),
+    // + A * step (step tables); -1: no such row / no numeraire table
+    constexpr int kFlush = (4 * AMAX + 1 + 31) / 32;
+    int flushBase[kFlush], flushMul[kFlush];
+    if (AAD) {
+#pragma unroll
+        for (int q = 0; q < kFlush; ++q) {
+            const int r = lane + 32 * q;
+            if (r < A) { flushBase[q] = oFf + r; flushMul[q] = 0; }
+            else if (r == A) { flushBase[q] = a.num ? oNum : -1; flushMul[q] = 1; }
+            else if (r < nTabRows) { const int t = (r - rFwd) / A; flushBase[q] = (t == 0 ? oFwd : t == 1 ? oDrift : oStd) + (r - rFwd - t * A); flushMul[q] = 2; }
+            else { flushBase[q] = -1; flushMul[q] = 2; }
+        }
+    }
     const double inv2s = 1.0 / (2.0 * a.smooth), invStrike = 1.0 / a.strike, cpn = a.coupon * a.cpn_dt;
 
     // contiguous batches per block: a thread's next path is kT / 2 antithetic pairs after its last one
@@ -340,6 +373,9 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
             if (batch == bBeg) mrgStart.init(a.seed1, a.seed2, pabs >> 1, a.mrg_jump);
             else mrgStart.advance(uint64_t(kT / 2), a.mrg_jump);
             mrg = mrgStart;
+            if (share) {
+                hs0 = parity ? mrgStart.y0 : mrgStart.x0; hs1 = parity ? mrgStart.y1 : mrgStart.x1; hs2 = parity ? mrgStart.y2 : mrgStart.x2;
+            }
             sign = (pabs & 1ull) ? -1.0 : 1.0;
         }
 
@@ -366,7 +402,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
                 double worst = S[0] * ec[0];
 #pragma unroll
                 for (int k = 1; k < AMAX; ++k)
-                    if (CF_DLM_HAS(k)) worst = fmin(worst, S[k] * ec[k]);
+                    if (CF_DLM_HAS(k)) { const double pf = S[k] * ec[k]; worst = pf < worst ? pf : worst; }
                 pay = fma(alive * cpn, cn, pay);
                 if (e < E - 1) {
                     const double f = fmin(1.0, fmax(0.0, (a.ko + a.smooth - worst) * inv2s));
@@ -407,7 +443,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
             fillGauss(i);
             double w[AMAX];
 #pragma unroll
-            for (int k = 0; k < AMAX; ++k) w[k] = sign * gq[k * 32 + lane];      // rows past A: never used
+            for (int k = 0; k < AMAX; ++k) w[k] = CF_DLM_HAS(k) ? sign * gq[k * 32 + lane] : 0.0;
             double* h = AAD ? a.hist + size_t(uint32_t(i) * hRows) * nSlots + slot : nullptr;
             if (AAD) {
                 h[(2u * uint32_t(A)) * nSlots] = alive;
@@ -507,13 +543,13 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
             };
             // sums of rows [0, nRows) over the warp's paths -> the warp's table; event rows first, then the step's
             auto flushRows = [&](int nRows, int ev, int i) {
-                for (int r = lane; r < nRows; r += 32) {
-                    const double s = dlm_row_sum(scr + r * kDlmRow);
-                    int o;
-                    if (r < A) o = oFf + ev * A + r;
-                    else if (r == A) o = a.num ? oNum + ev : -1;
-                    else { const int t = (r - rFwd) / A; o = (t == 0 ? oFwd : t == 1 ? oDrift : oStd) + i * A + (r - rFwd - t * A); }
-                    if (o >= 0) atomicAdd(myTab + o, s);
+#pragma unroll
+                for (int q = 0; q < kFlush; ++q) {
+                    const int r = lane + 32 * q;
+                    if (r < nRows && flushBase[q] >= 0) {
+                        const double s = dlm_row_sum(scr + r * kDlmRow);
+                        dlm_red(myTab + flushBase[q] + (flushMul[q] == 0 ? ev * A : flushMul[q] == 1 ? ev : i * A), s);
+                    }
                 }
             };
 
@@ -546,9 +582,9 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
                         const double fwdbar = normal ? sb : sb * ex;              // S = fwd + std cw | (fwd + sa) e - sa
                         const double xbar = normal ? 0.0 : sb * (Sn[k] + ac.x);
                         const double y = normal ? sb : xbar;
-                        if (ac.y >= 2.0) {                                        // alpha: +-(e - 1) sb
+                        if (ac.y >= 2.0) {                                        // alpha: +-(e - 1) sb; thread-private column: program order
                             const double t = sb * (ex - 1.0);
-                            alphaCol[k * kT + tid] += ac.y == 2.0 ? t : -t;
+                            dlm_red(a.alpha_cols + size_t(uint32_t(k) * nSlots) + slot, ac.y == 2.0 ? t : -t);
                         }
                         scr[(rFwd + k) * kDlmRow + lane] = fwdbar * Sp;
                         scr[(rDrift + k) * kDlmRow + lane] = xbar;
@@ -601,7 +637,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
 #pragma unroll
             for (int k = 0; k < AMAX; ++k) if (CF_DLM_HAS(k)) scr[k * kDlmRow + lane] = Sbar[k];
             __syncwarp();
-            if (lane < A) atomicAdd(myTab + oSpot + lane, dlm_row_sum(scr + lane * kDlmRow));
+            if (lane < A) dlm_red(myTab + oSpot + lane, dlm_row_sum(scr + lane * kDlmRow));
             __syncwarp();
         }
     }
@@ -626,11 +662,13 @@ __global__ void __launch_bounds__(NW * 32, 1) dlm_kernel(const LArgs a)
             for (int w = 0; w < NW; ++w) t += __ldcg(blockTab + size_t(w) * tabStride + oSpot + k);
             adj[k] = t;
             double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
-            if (hasAlpha)
+            if (hasAlpha) {
+                const double* col = a.alpha_cols + size_t(uint32_t(k) * nSlots) + size_t(blockIdx.x) * kT;
                 for (int c = 0; c < kT; c += 4) {
-                    u0 += alphaCol[k * kT + c]; u1 += alphaCol[k * kT + c + 1];
-                    u2 += alphaCol[k * kT + c + 2]; u3 += alphaCol[k * kT + c + 3];
+                    u0 += __ldcg(col + c); u1 += __ldcg(col + c + 1);
+                    u2 += __ldcg(col + c + 2); u3 += __ldcg(col + c + 3);
                 }
+            }
             adj[A + k] = (u0 + u1) + (u2 + u3);
         }
         for (int k = tid; k < A * A; k += kT) adj[2 * A + k] = 0.0;

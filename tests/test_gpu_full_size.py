@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import rel_err
-from test_gpu_europeans import config4
+from test_gpu_europeans import config4, check_multi
 from test_gpu_multi import config5, check_risks
 
 pytestmark = pytest.mark.gpu
@@ -41,3 +41,11 @@ def test_config4_full_size_properties(cf):
     scale = np.max(np.abs(r1)) + np.max(np.abs(r2))
     assert np.max(np.abs(r3 - (2.0 * r1 - 0.5 * r2))) < 1e-10 * scale
     assert abs(rv1 - float(w1 @ pv1)) < 1e-11 * np.abs(w1 * pv1).sum()
+
+
+def test_config4_itemised_risk_matrix_vs_reference_at_65536_paths(cf, ref):
+    """AADriskMulti of config 4 (1081 parameters x 720 payoffs) against the reference's own matrix on 2^16 mrg32k3a
+    paths -- the size the reference finishes in seconds on the box's host cores (its sweep is one pass per payoff)."""
+    npay = config4(cf); config4(ref)
+    risks = check_multi(cf, ref, "dup4", "eurs4", 1 << 16, False, [0, 59, 5 * 60 + 31, 719])
+    assert risks.shape == (1081, npay)

@@ -270,6 +270,31 @@ __device__ __forceinline__ double block_sum(double v, double* scratch)
     return s;
 }
 
+// Payoff sums of a call ladder over the 32 paths of a warp: sum over paths p of max(F_p - K_k, 0) / num for the strikes
+// k < n.  The forwards go through 32 doubles of shared memory once and lane l adds the paths, in path order, for the
+// strikes l, l + 32, ...: one pass instead of a five-level shuffle tree per strike.  All lanes must call together; a lane
+// without a path contributes nothing.  myPay: the warp's row of payoff sums at the ladder's first strike.
+__device__ __forceinline__ void warp_ladder_sums(double* fw, double F, bool valid, const double* __restrict__ K, int n,
+                                                 double num, double* myPay, int lane)
+{
+    __syncwarp();
+    fw[lane] = valid ? F : -1.0e300;                 // max(-1e300 - K, 0) = 0
+    __syncwarp();
+    const double2* f2 = reinterpret_cast<const double2*>(fw);
+    for (int k = lane; k < n; k += 32) {
+        const double strike = K[k];
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const double2 f = f2[p];                 // every lane reads the same address: one broadcast
+            s0 += fmax(f.x - strike, 0.0);
+            s1 += fmax(f.y - strike, 0.0);
+        }
+        const double s = s0 + s1;
+        myPay[k] += (num == 1.0) ? s : s / num;
+    }
+}
+
 // Keyed warp accumulation (the scatter of knot adjoints): every lane adds (a, b) to row[key].
 // Lanes sharing a key are serialised in lane order, so the result is bit-reproducible.
 // row: this warp's private smem row of nbins double2, zeroed here.

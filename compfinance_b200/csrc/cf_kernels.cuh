@@ -106,6 +106,7 @@ struct SampleAdj { double fwd, num, disc, lib; };
 // and, on request, to the per-path matrix.
 struct PayCtx {
     double*       myPay;       // this warp's [n_payoffs] row in shared memory
+    double*       fw;          // this warp's 32 doubles of shared scratch (call ladders)
     const double* w;           // aggregate weights or null
     double*       perPath;     // this path's [n_payoffs] row or null
     double        agg;
@@ -117,6 +118,18 @@ struct PayCtx {
         if (lane == 0) myPay[k] += s;
         if (w) agg += __ldg(w + k) * v;
         if (perPath) perPath[k] = v;
+    }
+    // calls max(F - K_k, 0) / num of the strikes k0 .. k0 + n - 1 (device memory), all lanes together
+    __device__ __forceinline__ void ladder(int k0, int n, const double* __restrict__ K, double F, double num)
+    {
+        warp_ladder_sums(fw, F, valid, K + k0, n, num, myPay + k0, lane);
+        if (w || perPath) {
+            for (int k = k0; k < k0 + n; ++k) {
+                const double v = div_n(fmax(F - __ldg(K + k), 0.0), num);
+                if (w) agg += __ldg(w + k) * v;
+                if (perPath) perPath[k] = v;
+            }
+        }
     }
 };
 
@@ -221,8 +234,8 @@ template <> struct Product<CF_PRODUCT_EUROPEANS> {
     template <class Src> __device__ void observe(int e, int nEvents, Src& s, PayCtx& c)
     {
         const double F = s.fwd(), num = s.num();
-        const int k1 = __ldg(off + e + 1);
-        for (int k = __ldg(off + e); k < k1; ++k) c.emit(k, div_n(fmax(F - __ldg(K + k), 0.0), num));
+        const int k0 = __ldg(off + e), k1 = __ldg(off + e + 1);
+        c.ladder(k0, k1 - k0, K, F, num);
     }
     __device__ void payoffs(double*) const {}
     __device__ void begin_reverse(const double*) {}
@@ -344,7 +357,7 @@ __host__ __device__ inline SmemSizes smem_sizes(int nSteps, int nKnots, int nEve
     // wrow (reverse sweep) aliases gq + tagq (forward sweep): the two phases never overlap within a block
     if (s.gq + s.tagq < s.wrow) s.gq = s.wrow - s.tagq;
     s.isev = align16(s.isev);
-    s.pay = align16(sizeof(double) * kWarps * size_t(nPayRows));
+    s.pay = align16(sizeof(double) * kWarps * (size_t(nPayRows) + (nPayRows > 0 ? 32 : 0)));      // + the ladders' scratch
     s.total = s.tabA + s.tabB + s.invdx + s.adj + s.red + s.gq + s.tagq + s.dirlow + s.base + s.lut + s.isev + s.pay;
     return s;
 }
@@ -561,6 +574,7 @@ __global__ void __launch_bounds__(kBlock, 2) path_kernel(const KArgs a)
         prd.init(a);
         PayCtx ctx;
         ctx.myPay = sm.pay + size_t(warp) * nPayRows; ctx.w = AAD ? a.wlong : nullptr;
+        ctx.fw = sm.pay + size_t(kWarps) * nPayRows + size_t(warp) * 32;
         ctx.perPath = (valid && a.per_path_payoffs) ? a.per_path_payoffs + p * a.n_payoffs : nullptr;
         ctx.agg = 0.0; ctx.valid = valid; ctx.lane = lane;
         int e = 0;

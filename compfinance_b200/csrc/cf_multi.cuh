@@ -57,7 +57,7 @@ __host__ __device__ inline MSmem multi_smem(int D, int m, int nPay, int dim, boo
     s.invdx = align16(sizeof(double) * m);
     s.ks = align16(sizeof(double) * size_t(nPay));
     s.isev = align16(size_t(D) + 1);
-    s.pay = align16(sizeof(double) * kWarps * size_t(nPay));
+    s.pay = align16(sizeof(double) * kWarps * (size_t(nPay) + 32));          // + 32 doubles per warp: the ladders' scratch
     s.gq = align16(sizeof(double) * kWarps * kChunk * 32);
     s.tagq = align16(sizeof(uint16_t) * kWarps * kChunk * 32);
     s.dirlow = sobol ? align16(sizeof(uint32_t) * size_t(dim) * kLowBits) : 0;
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
     if (kSobol) sobol_load_low(dirlow, a.sobol_dir, a.dim);
     __syncthreads();
     double* myPay = payRows + size_t(warp) * nPay;
+    double* fw = payRows + size_t(kWarps) * nPay + size_t(warp) * 32;
 
     Locator loc;
     loc.x = xs; loc.lut = nullptr; loc.m = m; loc.lutN = 0; loc.x0 = 0.0; loc.scale = 0.0;
@@ -131,12 +132,10 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
         auto sample = [&](int e, int nst, double L) {
             const double S = exp(L);
             const int k0 = a.koff[e], k1 = a.koff[e + 1];
-            for (int k = k0; k < k1; ++k) {
-                const double v = fmax(S - ks[k], 0.0);            // Dupire leaves the numeraire at 1 (mcBase.h:91-99)
-                const double s = warp_sum(valid ? v : 0.0);
-                if (lane == 0) myPay[k] += s;
-                if (valid && a.per_path_payoffs) a.per_path_payoffs[pidx * nPay + k] = v;
-            }
+            // payoff sums of the maturity's strike ladder; Dupire leaves the numeraire at 1 (mcBase.h:91-99)
+            warp_ladder_sums(fw, S, valid, ks + k0, k1 - k0, 1.0, myPay + k0, lane);
+            if (valid && a.per_path_payoffs)
+                for (int k = k0; k < k1; ++k) a.per_path_payoffs[pidx * nPay + k] = fmax(S - ks[k], 0.0);
             // class = #strikes strictly below S (max(x, 0) has derivative 1 iff x > 0, AADExpr.h:571-583)
             int lo = k0, hi = k1;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks[mid] < S) lo = mid + 1; else hi = mid; }

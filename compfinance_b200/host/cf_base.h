@@ -30,6 +30,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/cf_b200.h"
@@ -255,11 +256,34 @@ struct CfSession
     CfDeviceSetup                  setup;     // PODs point into its own vectors: a session is never moved
     cf_plan*                       plan = nullptr;
     size_t                         nAdj = 0, nPay = 0;
+    // device adjoint q lands on parameter directParam[q] itself (-1: on nothing); directState 1: that holds for every
+    // target, the host tape has nothing to propagate (Dupire with its time map: spot and local vols); -1: it does not
+    std::vector<int>               directParam;
+    int                            directState = 0;
     CfSession() = default;
     CfSession(const CfSession&) = delete;
     CfSession& operator=(const CfSession&) = delete;
     ~CfSession() { if (plan) cf_plan_destroy(plan); }
 };
+
+// Are the targets of the device adjoints the model's parameters themselves?  Then the sweep mark -> start of
+// mcBase.h:518 only visits nodes with zero adjoints and the risks are the device sums, added in the same order.
+inline bool cfDirectTargets(CfSession& s, const std::vector<Number*>& params)
+{
+    if (s.directState == 0) {
+        const auto& targets = s.setup.mdl.adjointTargets;
+        std::unordered_map<const Number*, int> where;
+        for (size_t j = 0; j < params.size(); ++j) where.emplace(params[j], int(j));
+        s.directParam.assign(targets.size(), -1);
+        s.directState = 1;
+        for (size_t q = 0; q < targets.size() && s.directState == 1; ++q) {
+            if (!targets[q]) continue;
+            const auto it = where.find(targets[q]);
+            if (it == where.end()) s.directState = -1; else s.directParam[q] = it->second;
+        }
+    }
+    return s.directState == 1;
+}
 
 // Number::tape points at the session's tape while the session is worked on
 struct CfTapeScope
@@ -448,13 +472,19 @@ inline AADSums cfSimulAADSums(const Product<Number>& prd, const Model<Number>& m
 
     const auto t2 = now();
     // AAD - 4 (mcBase.h:512-527): adjoints accumulated over paths on the pre-mark nodes, one sweep mark -> start
-    s->tape.resetAdjoints();
-    const auto& targets = s->setup.mdl.adjointTargets;
-    for (size_t k = 0; k < nAdj; ++k)
-        if (targets[k]) targets[k]->adjoint() += adj[k];
-    Number::propagateMarkToStart();
-    out.risks.resize(nParam);
-    for (size_t j = 0; j < nParam; ++j) out.risks[j] = params[j]->adjoint() / double(nPath);
+    out.risks.assign(nParam, 0.0);
+    if (cfDirectTargets(*s, params)) {
+        for (size_t k = 0; k < nAdj; ++k)
+            if (s->directParam[k] >= 0) out.risks[size_t(s->directParam[k])] += adj[k];
+        for (size_t j = 0; j < nParam; ++j) out.risks[j] /= double(nPath);
+    } else {
+        s->tape.resetAdjoints();
+        const auto& targets = s->setup.mdl.adjointTargets;
+        for (size_t k = 0; k < nAdj; ++k)
+            if (targets[k]) targets[k]->adjoint() += adj[k];
+        Number::propagateMarkToStart();
+        for (size_t j = 0; j < nParam; ++j) out.risks[j] = params[j]->adjoint() / double(nPath);
+    }
     if (timing) std::fprintf(stderr, "cfSimulAADSums: session (clone + init on tape + images + plan, or reuse) %.0f us, device run %.0f us, chain rule %.0f us\n",
                              us(t0, t1), us(t1, t2), us(t2, now()));
     return out;
@@ -522,6 +552,18 @@ inline AADMultiSums cfSimulAADMultiSums(const Product<Number>& prd, const Model<
 
     const auto& targets = s->setup.mdl.adjointTargets;
     out.risks.resize(nParam, nPay);
+    if (cfDirectTargets(*s, params)) {
+        for (size_t j = 0; j < nParam; ++j) std::fill(out.risks[j], out.risks[j] + nPay, 0.0);
+        for (size_t q = 0; q < nAdj; ++q) {
+            if (s->directParam[q] < 0) continue;
+            double* row = out.risks[size_t(s->directParam[q])];
+            const double* src = tables.data() + q * nPay;
+            for (size_t k = 0; k < nPay; ++k) row[k] += src[k];
+        }
+        for (size_t j = 0; j < nParam; ++j)
+            for (size_t k = 0; k < nPay; ++k) out.risks[j][k] /= double(nPath);
+        return out;
+    }
     for (size_t k = 0; k < nPay; ++k) {
         s->tape.resetAdjoints();
         for (size_t q = 0; q < nAdj; ++q)

@@ -269,7 +269,7 @@ def run_config(args):
         kernel_ms = float(km.item())
         value = n_paths / (kernel_ms * 1e-3)                     # device time of the path kernels (max over ranks)
         fp64_peak = eng.fp64_peak_tflops()
-        achieved = value * flops / 1e12
+        achieved = value * flops / 1e12 / world                  # per GPU: the peak is one GPU's
         cpu = None
         if not args.no_cpu_baseline:
             try:
@@ -301,7 +301,7 @@ def run_config(args):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": None, "kernel_ms": kernel_ms, "algorithmic_flops_per_path": flops,
                          "peak_source": "measured here: scalar DFMA microbenchmark cf_measure_fp64_peak",
-                         "note": "value and kernel_ms are the device time of the path kernels of the call (CUDA events on the launch stream, max over ranks); e2e is the wall time of the call"},
+                         "note": "value and kernel_ms are the device time of the path kernels of the call (CUDA events on the launch stream, max over ranks); achieved is per GPU; e2e is the wall time of the call"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

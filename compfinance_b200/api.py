@@ -20,7 +20,7 @@ EXPORTED = [
     "cfx_put_european", "cfx_put_barrier", "cfx_put_contingent", "cfx_put_europeans", "cfx_put_displaced", "cfx_put_multistats",
     "cfx_put_baskets", "cfx_put_autocall", "cfx_num_payoffs", "cfx_num_params",
     "cfx_payoff_labels", "cfx_param_labels", "cfx_product_timeline", "cfx_value", "cfx_simul_paths",
-    "cfx_aad_risk_one", "cfx_simul_aad_paths", "cfx_aad_risk_aggregate", "cfx_aad_risk_multi", "cfx_bump_risk", "cfx_dupire_aad_risk", "cfx_dupire_calib", "cfx_dupire_superbucket",
+    "cfx_aad_risk_one", "cfx_simul_aad_paths", "cfx_simul_aad_multi_paths", "cfx_aad_risk_aggregate", "cfx_aad_risk_multi", "cfx_bump_risk", "cfx_dupire_aad_risk", "cfx_dupire_calib", "cfx_dupire_superbucket",
     "cfx_describe", "cfx_rng_sequence",
 ]
 
@@ -198,6 +198,15 @@ class CompFinance:
                                                   C.c_int(seed2), C.c_int(n_path), C.c_int(int(parallel)),
                                                   pv.ctypes.data_as(_dp), C.byref(rv), risks.ctypes.data_as(_dp)))
         return pv, rv.value, risks
+
+    def simul_aad_multi_paths(self, model, product, n_path, sobol=True, parallel=True, seed1=12345, seed2=12346):
+        """mcSimulAADMulti (mcBase.h:776): per-path payoffs [nPath][nPay] and risks [nParam][nPay] (sums over paths / nPath)."""
+        npay, npar = self.num_payoffs(product), self.num_params(model)
+        pays, risks = np.empty((n_path, npay)), np.empty((npar, npay))
+        self._chk(self.lib.cfx_simul_aad_multi_paths(model.encode(), product.encode(), C.c_int(int(sobol)), C.c_int(seed1),
+                                                     C.c_int(seed2), C.c_int(n_path), C.c_int(int(parallel)),
+                                                     pays.ctypes.data_as(_dp), risks.ctypes.data_as(_dp)))
+        return pays, risks
 
     def aad_risk_multi(self, model, product, n_path, sobol=True, parallel=True, seed1=12345, seed2=12346):
         """AADriskMulti (main.h:269): values [nPay], risks [nParam][nPay]."""

@@ -22,6 +22,7 @@ UNITS = {
     "cf_tables.cpp": ["cf_tables.h", "joe_kuo_init.inc"],
 }
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS += os.environ.get("CF_NVCC_EXTRA", "").split()      # experiments: e.g. CF_NVCC_EXTRA="-DCF_REVS_WARPS=12"
 
 
 def _stale(target, deps):

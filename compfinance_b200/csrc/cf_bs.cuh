@@ -22,7 +22,10 @@
 
 namespace cf {
 
-constexpr int kBsRevWarps = 16;
+#ifndef CF_BS_REV_WARPS
+#define CF_BS_REV_WARPS 24                   // measured on config 2: 16 warps (128 registers) 0.363 ms, 20: 0.345, 24 (80 registers): 0.336, 32 (64): 0.365
+#endif
+constexpr int kBsRevWarps = CF_BS_REV_WARPS;
 constexpr int kBsRevBlock = kBsRevWarps * 32;
 constexpr int kBsMaxWords = 1024;              // live-mask words (32 paths each) one block can own
 

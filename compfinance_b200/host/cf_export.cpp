@@ -269,6 +269,24 @@ int cfx_aad_risk_multi(const char* modelId, const char* productId, int useSobol,
     });
 }
 
+// Per-path results of mcSimulAADMulti / mcParallelSimulAADMulti (mcBase.h:776, 859): payoffs [nPath][nPay] (the matrix the
+// reference's result carries, mcBase.h:758-771), risks [nParam][nPay]
+int cfx_simul_aad_multi_paths(const char* modelId, const char* productId, int useSobol, int seed1, int seed2, int numPath,
+                              int parallel, double* payoffs, double* risks)
+{
+    return guarded([&] {
+        const Model<Number>* mdl = getModel<Number>(modelId);
+        const Product<Number>* prd = getProduct<Number>(productId);
+        if (!mdl || !prd) throw std::runtime_error("model / product not found");
+        auto rng = cfdrv::makeRng(mkNum(parallel, useSobol, numPath, seed1, seed2));
+        auto res = parallel ? mcParallelSimulAADMulti(*prd, *mdl, *rng, numPath) : mcSimulAADMulti(*prd, *mdl, *rng, numPath);
+        const size_t nPay = prd->payoffLabels().size();
+        if (res.payoffs.size() != size_t(numPath)) throw std::runtime_error("mcSimulAADMulti: per-path payoffs not filled (too large)");
+        for (size_t i = 0; i < res.payoffs.size(); ++i) std::copy(res.payoffs[i].begin(), res.payoffs[i].end(), payoffs + i * nPay);
+        std::copy(res.risks.begin(), res.risks.end(), risks);
+    });
+}
+
 // xBumprisk (xlExport.cpp:876-922) -> bumpRisk (main.h:316): risks[nParam][nPay]
 int cfx_bump_risk(const char* modelId, const char* productId, int useSobol, int seed1, int seed2, int numPath,
                   int parallel, double* values, double* risks)

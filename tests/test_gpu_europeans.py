@@ -194,3 +194,18 @@ def test_bump_risk_vs_reference_bump_driver(cf, ref):
     assert rel_err(values, values_r) < PRICE_TOL
     assert bumps.shape == bumps_r.shape == (4, 2)
     assert np.max(np.abs(bumps - bumps_r)) < 1e-5 * max(1.0, float(np.max(np.abs(bumps_r))))
+
+
+def test_mc_simul_aad_multi_carries_the_per_path_payoffs(cf, ref):
+    """mcSimulAADMulti's result holds the nPath x nPay payoff matrix like the reference's (mcBase.h:758-771): callers
+    that average results.payoffs (main.h:269-312) get the values; its risks are AADriskMulti's."""
+    spots, times, vols = config3_surface()
+    for api in (cf, ref):
+        api.put_dupire(100.0, spots, times, vols, 0.25, "dupmp")
+        api.put_europeans([0.5, 0.5, 1.0, 1.0, 1.0], [95.0, 105.0, 90.0, 100.0, 110.0], "eursmp")
+    n = 2500
+    pays, risks = cf.simul_aad_multi_paths("dupmp", "eursmp", n, sobol=False)
+    assert pays.shape == (n, 5) and np.max(np.abs(pays - ref.simul_paths("dupmp", "eursmp", n, sobol=False))) < 1e-9
+    values, multi = cf.aad_risk_multi("dupmp", "eursmp", n, sobol=False)
+    assert rel_err(pays.mean(axis=0), values) < 1e-12
+    check_risks(risks, multi)

@@ -430,3 +430,19 @@ def test_invalid_descriptors(eng):
         eng.run_value(mdl, prd_bad, eng.rng("sobol"), 0, 100)
     with pytest.raises(CfError, match="n_paths"):
         eng.run_value(mdl, prd, eng.rng("sobol"), 0, 0)
+
+
+def test_black_scholes_barrier_fast_path_large_and_ragged_runs(cf, ref):
+    """The Black-Scholes barrier path of its own (shared forward kernel with the log-normal step, lane-parallel reverse
+    over contiguous live ranges): a run longer than one launch (2^21 + 4097 paths), a ragged small one and a mid-size
+    one (one path per thread), against the reference with both generators; puts, a discounted late settlement."""
+    for api in (cf, ref):
+        (api.put_black_scholes if api is cf else api.put_bs)(100.0, 0.22, False, 0.03, 0.01, "bsfp")
+        api.put_barrier(105.0, 135.0, 1.0, 1.0 / 52, 0.5, False, "uocfp")
+        api.put_barrier(95.0, 140.0, 1.0, 1.0 / 52, 1.0, True, "uopfp")
+    for prd, n, sobol in [("uocfp", (1 << 21) + 4097, True), ("uocfp", 4097, False), ("uopfp", 150_001, False), ("uopfp", 257, True)]:
+        pv, rv, risks = cf.aad_risk_one("bsfp", prd, n, risk_payoff=0, sobol=sobol)
+        pv_r, rv_r, risks_r = ref.aad_risk_one("bsfp", prd, n, risk_payoff=0, sobol=sobol)
+        assert rel_err(pv, pv_r) < PRICE_TOL and abs(rv / rv_r - 1) < PRICE_TOL
+        assert rel_err(risks, risks_r) < RISK_TOL
+        assert rel_err(cf.value("bsfp", prd, n, sobol=sobol), ref.value("bsfp", prd, n, sobol=sobol)) < PRICE_TOL

@@ -457,7 +457,7 @@ def main():
                 "unit": "paths/s", "price": wres[2] / (N_PATHS * world)}
 
     # ---- e2e: the call a user makes (dupireAADRisk through the host API, host buffers in and out)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, args.steps)                              # as many end-to-end calls as timed steps: the closing barrier is amortised alike
     # host -> device per call: the notionals (kernel parameters); the model's tables went up when the session of this
     # (model, product, RNG) was built by the first call after putDupire / putBarrier and stay resident (cf_base.h).
     # e2e["first_call"] times the other regime: the session dropped before every call (clone, init() on the host tape,

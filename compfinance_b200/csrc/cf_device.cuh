@@ -270,6 +270,14 @@ __device__ __forceinline__ double block_sum(double v, double* scratch)
     return s;
 }
 
+// max(d, 0) for a finite d in three integer operations on the two halves (fmax carries NaN handling: nine)
+__device__ __forceinline__ double pos_part(double d)
+{
+    const int hi = __double2hiint(d);
+    const int keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, __double2loint(d) & keep);
+}
+
 // Payoff sums of a call ladder over the 32 paths of a warp: sum over paths p of max(F_p - K_k, 0) / num for the strikes
 // k < n.  The forwards go through 32 doubles of shared memory once and lane l adds the paths, in path order, for the
 // strikes l, l + 32, ...: one pass instead of a five-level shuffle tree per strike.  All lanes must call together; a lane
@@ -281,14 +289,16 @@ __device__ __forceinline__ void warp_ladder_sums(double* fw, double F, bool vali
     fw[lane] = valid ? F : -1.0e300;                 // max(-1e300 - K, 0) = 0
     __syncwarp();
     const double2* f2 = reinterpret_cast<const double2*>(fw);
+    // one strike per pass, not unrolled further: the body is 16 pairs already and code size matters (instruction cache)
+#pragma unroll 1
     for (int k = lane; k < n; k += 32) {
         const double strike = K[k];
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
             const double2 f = f2[p];                 // every lane reads the same address: one broadcast
-            s0 += fmax(f.x - strike, 0.0);
-            s1 += fmax(f.y - strike, 0.0);
+            s0 += pos_part(f.x - strike);
+            s1 += pos_part(f.y - strike);
         }
         const double s = s0 + s1;
         myPay[k] += (num == 1.0) ? s : s / num;

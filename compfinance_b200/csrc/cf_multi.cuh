@@ -127,15 +127,18 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
             gen.sign = (pabs & 1ull) ? -1.0 : 1.0;
         }
 
-        double Lh[kMultiMaxSteps], gh[kMultiMaxSteps];
+        double Lh[kMultiMaxSteps + 1], gh[kMultiMaxSteps];     // log-spot at every timeline point, Gaussian of every step
         // sample of event e after nst steps at log-spot L: payoffs, then the sweep of its strike class
         auto sample = [&](int e, int nst, double L) {
             const double S = exp(L);
             const int k0 = a.koff[e], k1 = a.koff[e + 1];
             // payoff sums of the maturity's strike ladder; Dupire leaves the numeraire at 1 (mcBase.h:91-99)
             warp_ladder_sums(fw, S, valid, ks + k0, k1 - k0, 1.0, myPay + k0, lane);
-            if (valid && a.per_path_payoffs)
+            if (valid && a.per_path_payoffs) {
+                // rarely taken: kept out of the instruction cache's way
+#pragma unroll 1
                 for (int k = k0; k < k1; ++k) a.per_path_payoffs[pidx * nPay + k] = fmax(S - ks[k], 0.0);
+            }
             // class = #strikes strictly below S (max(x, 0) has derivative 1 iff x > 0, AADExpr.h:571-583)
             int lo = k0, hi = k1;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks[mid] < S) lo = mid + 1; else hi = mid; }
@@ -177,8 +180,6 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
         };
 
         double X = logS0;
-        int e = 0;
-        if (isev[0]) { sample(e, 0, X); ++e; }
         for (int i0 = 0; i0 < D; i0 += kChunk) {
             const int cnt = min(kChunk, D - i0);
             gen.fill(i0, cnt);
@@ -192,9 +193,15 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
                 if (b.side != 0) v = y[b.side > 0 ? m - 1 : 0];
                 else { const double y1 = y[b.n]; v = y1 + (y[b.n + 1] - y1) * ((X - xs[b.n]) * invdx[b.n]); }
                 X += v * (-0.5 * v + g);                              // mcMdlDupire.h:271
-                if (isev[i + 1]) { sample(e, i + 1, X); ++e; }
             }
         }
+        Lh[D] = X;
+        // the samples after the path, from ONE call site: inlined into the (unrolled) step loop the sweep was replicated
+        // nine times, 190 KB of code, and the kernel waited on instruction fetch four cycles out of five
+        int e = 0;
+#pragma unroll 1
+        for (int pt = 0; pt <= D; ++pt)
+            if (isev[pt]) { sample(e, pt, Lh[pt]); ++e; }
     }
 
     __syncthreads();

@@ -727,6 +727,10 @@ struct DevPlan {
         // the coarse part: |x| 2^10 n < 2^62 with |x| up to ~ 2^10 spot
         if (std::ldexp(double(n) * std::fabs(spot0), 20) >= std::ldexp(1.0, 62)) throw CfError("cf_b200: spot x paths too large for the fixed-point accumulators of the itemised risk");
         cf::MArgs a{};
+        // batches dealt round-robin over the blocks: measured 8.2 ms against 9.5 ms with contiguous ranges and incremental
+        // jumps (config 4, 2^22 paths) -- the opposite of the generic kernel; CF_MULTI_STRIDED=0 switches
+        static const int strided = [] { const char* e = std::getenv("CF_MULTI_STRIDED"); return e ? std::atoi(e) : 1; }();
+        a.strided = strided;
         a.first_path = first; a.n_paths = n; a.n_batches = int(nb64);
         a.seed1 = base.seed1; a.seed2 = base.seed2; a.dim = dim;
         a.sobol_dir = sobolDir.p; a.mrg_jump = mrgJump.p;

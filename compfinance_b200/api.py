@@ -20,7 +20,7 @@ EXPORTED = [
     "cfx_put_european", "cfx_put_barrier", "cfx_put_contingent", "cfx_put_europeans", "cfx_put_displaced", "cfx_put_multistats",
     "cfx_put_baskets", "cfx_put_autocall", "cfx_num_payoffs", "cfx_num_params",
     "cfx_payoff_labels", "cfx_param_labels", "cfx_product_timeline", "cfx_value", "cfx_simul_paths",
-    "cfx_aad_risk_one", "cfx_simul_aad_paths", "cfx_simul_aad_multi_paths", "cfx_aad_risk_aggregate", "cfx_aad_risk_multi", "cfx_bump_risk", "cfx_dupire_aad_risk", "cfx_dupire_calib", "cfx_dupire_superbucket",
+    "cfx_aad_risk_one", "cfx_simul_aad_paths", "cfx_simul_aad_multi_paths", "cfx_run_range", "cfx_aad_risk_aggregate", "cfx_aad_risk_multi", "cfx_bump_risk", "cfx_dupire_aad_risk", "cfx_dupire_calib", "cfx_dupire_superbucket",
     "cfx_describe", "cfx_rng_sequence",
 ]
 
@@ -207,6 +207,22 @@ class CompFinance:
                                                      C.c_int(seed2), C.c_int(n_path), C.c_int(int(parallel)),
                                                      pays.ctypes.data_as(_dp), risks.ctypes.data_as(_dp)))
         return pays, risks
+
+    def run_range(self, model, product, first_path, n_paths, weights=None, sobol=True, seed1=12345, seed2=12346, n_adjoints=0):
+        """Sums over the paths [first_path, first_path + n_paths) through cf_run_value (weights None) or cf_run_aad:
+        (payoff sums,) or (payoff sums, aggregate sum, table adjoints[n_adjoints])."""
+        npay = self.num_payoffs(product)
+        sums = np.empty(npay)
+        if weights is None:
+            self._chk(self.lib.cfx_run_range(model.encode(), product.encode(), C.c_int(0), C.c_int(int(sobol)), C.c_int(seed1), C.c_int(seed2),
+                                             C.c_ulonglong(first_path), C.c_ulonglong(n_paths), None, sums.ctypes.data_as(_dp), None, None))
+            return (sums,)
+        w, pw = _d(weights)
+        agg, adj = C.c_double(), np.empty(n_adjoints)
+        self._chk(self.lib.cfx_run_range(model.encode(), product.encode(), C.c_int(1), C.c_int(int(sobol)), C.c_int(seed1), C.c_int(seed2),
+                                         C.c_ulonglong(first_path), C.c_ulonglong(n_paths), pw, sums.ctypes.data_as(_dp), C.byref(agg),
+                                         adj.ctypes.data_as(_dp)))
+        return sums, agg.value, adj
 
     def aad_risk_multi(self, model, product, n_path, sobol=True, parallel=True, seed1=12345, seed2=12346):
         """AADriskMulti (main.h:269): values [nPay], risks [nParam][nPay]."""

@@ -394,6 +394,43 @@ int cfx_describe(const char* modelId, const char* productId, int aad, int* dims,
     });
 }
 
+// A range of paths [firstPath, firstPath + nPaths) of (model, product) straight through the C ABI (cf_run_value /
+// cf_run_aad): sums, not averages -- what one worker of the reference's parallel loops contributes (mcBase.h:346-395,
+// 640-746).  For tests of arbitrary shard boundaries (odd antithetic starts) on every model.  tableAdjoints: dims[4] of
+// cfx_describe doubles (AAD only); weights: the aggregate's payoff weights (AAD only).
+int cfx_run_range(const char* modelId, const char* productId, int aad, int useSobol, int seed1, int seed2,
+                  unsigned long long firstPath, unsigned long long nPaths, const double* weights, double* payoffSums,
+                  double* aggSum, double* tableAdjoints)
+{
+    return guarded([&] {
+        CfDeviceSetup s;
+        auto rng = cfdrv::makeRng(mkNum(1, useSobol, int(nPaths), seed1, seed2));
+        if (aad) {
+            const Model<Number>* mdl = getModel<Number>(modelId);
+            const Product<Number>* prd = getProduct<Number>(productId);
+            if (!mdl || !prd) throw std::runtime_error("model / product not found");
+            auto mn = mdl->clone();
+            mn->allocate(prd->timeline(), prd->defline());
+            Number::tape->clear();
+            mn->putParametersOnTape();
+            mn->init(prd->timeline(), prd->defline());
+            Number::tape->mark();
+            cfBuildImages(*prd, *mn, *rng, s);
+            cfCheck(cf_run_aad(&s.mdl.pod, &s.prd.pod, &s.rng, firstPath, nPaths, weights, payoffSums, aggSum, tableAdjoints, nullptr, nullptr));
+            Number::tape->clear();
+        } else {
+            const Model<double>* mdl = getModel<double>(modelId);
+            const Product<double>* prd = getProduct<double>(productId);
+            if (!mdl || !prd) throw std::runtime_error("model / product not found");
+            auto md = mdl->clone();
+            md->allocate(prd->timeline(), prd->defline());
+            md->init(prd->timeline(), prd->defline());
+            cfBuildImages(*prd, *md, *rng, s);
+            cfCheck(cf_run_value(&s.mdl.pod, &s.prd.pod, &s.rng, firstPath, nPaths, payoffSums, nullptr));
+        }
+    });
+}
+
 // Sequential RNG interface (RNG::init / skipTo / nextU / nextG, mcBase.h:228-246) served by the device
 int cfx_rng_sequence(int useSobol, int seed1, int seed2, int dim, unsigned skip, int n, int gaussian, double* out)
 {

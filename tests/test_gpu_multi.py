@@ -165,3 +165,23 @@ def test_multistats_has_no_device_aad(cf):
     cf.put_multistats(3, g["fix_dates"], g["fwd_dates"], "stats_t")
     with pytest.raises(RuntimeError):
         cf.aad_risk_one("dlm_t", "stats_t", 1024)
+
+
+@pytest.mark.parametrize("sobol", [False, True])
+def test_arbitrary_shard_boundaries_add_up_displaced_model(cf, sobol):
+    """Ranges of paths through the C ABI (first_path, n_paths) add up to the whole run whatever the boundaries: odd ones
+    split antithetic pairs of mrg32k3a across ranges (the kernel's lanes then no longer share a generator) and cut Sobol
+    windows; a range of one path; ranges longer than one batch."""
+    config5(cf)
+    n = 5000
+    nadj = cf.describe("dlm5", "auto5", aad=True)["adjoint_size"]
+    w = [1.0]
+    whole = cf.run_range("dlm5", "auto5", 0, n, w, sobol=sobol, n_adjoints=nadj)
+    cuts = [0, 1, 1001, 1002, 2345, 4999, n]
+    parts = [cf.run_range("dlm5", "auto5", a, b - a, w, sobol=sobol, n_adjoints=nadj) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert abs(sum(p[0][0] for p in parts) / whole[0][0] - 1) < 1e-13
+    assert abs(sum(p[1] for p in parts) / whole[1] - 1) < 1e-13
+    tot = sum(p[2] for p in parts)
+    assert np.max(np.abs(tot - whole[2])) < 1e-11 * np.max(np.abs(whole[2]))
+    vals = [cf.run_range("dlm5", "auto5", a, b - a, sobol=sobol)[0][0] for a, b in zip(cuts[:-1], cuts[1:])]
+    assert abs(sum(vals) / whole[0][0] - 1) < 1e-13

@@ -446,3 +446,26 @@ def test_black_scholes_barrier_fast_path_large_and_ragged_runs(cf, ref):
         assert rel_err(pv, pv_r) < PRICE_TOL and abs(rv / rv_r - 1) < PRICE_TOL
         assert rel_err(risks, risks_r) < RISK_TOL
         assert rel_err(cf.value("bsfp", prd, n, sobol=sobol), ref.value("bsfp", prd, n, sobol=sobol)) < PRICE_TOL
+
+
+@pytest.mark.parametrize("sobol", [False, True])
+def test_arbitrary_shard_boundaries_add_up_black_scholes_and_europeans(cf, sobol):
+    """cf_run_value / cf_run_aad over ranges with odd boundaries (antithetic pairs split, Sobol windows cut, a single path,
+    several batches per block) add up to the whole run: the Black-Scholes barrier path of its own and the generic
+    kernel with contiguous batches per block (incremental mrg32k3a jumps) on a ladder of Europeans."""
+    spots, times, vols = config3_surface()
+    cf.put_black_scholes(100.0, 0.2, False, 0.03, 0.01, "bsr")
+    cf.put_barrier(100.0, 130.0, 1.0, 1.0 / 52, 0.5, False, "uocr")
+    cf.put_dupire(100.0, spots, times, vols, 0.25, "dupr")
+    cf.put_europeans([0.5, 0.5, 1.0, 1.0, 1.0], [95.0, 105.0, 90.0, 100.0, 110.0], "eursr")
+    for model, product, w, n in [("bsr", "uocr", [1.0, 0.5], 70_001), ("dupr", "eursr", [1.0, -0.5, 0.25, 2.0, 1.0], 150_001)]:
+        nadj = cf.describe(model, product, aad=True)["adjoint_size"]
+        whole = cf.run_range(model, product, 0, n, w, sobol=sobol, n_adjoints=nadj)
+        cuts = [0, 1, 1001, 1002, 33_333, n - 1, n]
+        parts = [cf.run_range(model, product, a, b - a, w, sobol=sobol, n_adjoints=nadj) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert np.max(np.abs(sum(p[0] for p in parts) / whole[0] - 1)) < 1e-12
+        assert abs(sum(p[1] for p in parts) / whole[1] - 1) < 1e-12
+        tot = sum(p[2] for p in parts)
+        assert np.max(np.abs(tot - whole[2])) < 1e-10 * np.max(np.abs(whole[2]))
+        vals = sum(cf.run_range(model, product, a, b - a, sobol=sobol)[0] for a, b in zip(cuts[:-1], cuts[1:]))
+        assert np.max(np.abs(vals / whole[0] - 1)) < 1e-12

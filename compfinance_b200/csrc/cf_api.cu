@@ -738,8 +738,9 @@ struct DevPlan {
         a.interp_vols = tabA.p; a.log_spots = tabB.p;
         a.ksorted = mK.p; a.koff = eOff.p; a.n_payoffs = nPay; a.cmax = multiCmax;
         a.partial = mPartial.p; a.Thi = mThi.p; a.Tlo = mTlo.p; a.lo_scale = std::ldexp(1.0, loBits); a.per_path_payoffs = nullptr;
+        a.lut = lut.p; a.lut_n = lutN; a.lut_x0 = base.lut_x0; a.lut_scale = base.lut_scale;
         const bool sob = rngKind == CF_RNG_SOBOL;
-        const size_t smem = cf::multi_smem(D, m, nPay, dim, sob).total;
+        const size_t smem = cf::multi_smem(D, m, nPay, dim, sob, lutN).total;
         if (smem > kFastSmemLimit / 2) throw CfError("cf_run_aad_multi: tables do not fit in shared memory");
         auto fn = cf::pick_multi_kernel(rngKind);
         CF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

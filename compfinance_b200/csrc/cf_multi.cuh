@@ -46,11 +46,15 @@ struct MArgs {
     long long* Tlo;                // the remainders, fixed point 2^-lo_bits
     double   lo_scale;             // 2^lo_bits
     double*  per_path_payoffs;     // [n_paths][n_payoffs] (sorted order) or null
+    // bucket lookup by uniform cells, as in the generic kernel (KArgs::lut): 0 entries = binary search
+    const uint8_t* lut;
+    int      lut_n;
+    double   lut_x0, lut_scale;
 };
 
-struct MSmem { size_t y, x, invdx, ks, isev, pay, gq, tagq, dirlow, base, total; };
+struct MSmem { size_t y, x, invdx, ks, isev, pay, gq, tagq, dirlow, base, lut, total; };
 
-__host__ __device__ inline MSmem multi_smem(int D, int m, int nPay, int dim, bool sobol)
+__host__ __device__ inline MSmem multi_smem(int D, int m, int nPay, int dim, bool sobol, int lutN)
 {
     MSmem s{};
     s.y = align16(sizeof(double) * size_t(D) * m);
@@ -63,7 +67,8 @@ __host__ __device__ inline MSmem multi_smem(int D, int m, int nPay, int dim, boo
     s.tagq = align16(sizeof(uint16_t) * kWarps * kChunk * 32);
     s.dirlow = sobol ? align16(sizeof(uint32_t) * size_t(dim) * kLowBits) : 0;
     s.base = sobol ? align16(sizeof(uint32_t) * 2 * size_t(dim)) : 0;
-    s.total = s.y + s.x + s.invdx + s.ks + s.isev + s.pay + s.gq + s.tagq + s.dirlow + s.base;
+    s.lut = align16(size_t(lutN > 0 ? lutN : 1));
+    s.total = s.y + s.x + s.invdx + s.ks + s.isev + s.pay + s.gq + s.tagq + s.dirlow + s.base + s.lut;
     return s;
 }
 
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = a.D, m = a.m, nPay = a.n_payoffs;
     constexpr bool kSobol = (RNGK == CF_RNG_SOBOL);
-    const MSmem z = multi_smem(D, m, nPay, a.dim, kSobol);
+    const MSmem z = multi_smem(D, m, nPay, a.dim, kSobol, a.lut_n);
     unsigned char* p = smem_raw;
     double* ysm = reinterpret_cast<double*>(p);         p += z.y;
     double* xs = reinterpret_cast<double*>(p);          p += z.x;
@@ -85,7 +90,8 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
     double* gq = reinterpret_cast<double*>(p);          p += z.gq;
     uint16_t* tagq = reinterpret_cast<uint16_t*>(p);    p += z.tagq;
     uint32_t* dirlow = reinterpret_cast<uint32_t*>(p);  p += z.dirlow;
-    uint32_t* base = reinterpret_cast<uint32_t*>(p);
+    uint32_t* base = reinterpret_cast<uint32_t*>(p);    p += z.base;
+    uint8_t* lutS = reinterpret_cast<uint8_t*>(p);
 
     for (int i = tid; i < D * m; i += kBlock) ysm[i] = a.interp_vols[i];
     for (int i = tid; i < m; i += kBlock) xs[i] = a.log_spots[i];
@@ -93,13 +99,14 @@ __global__ void __launch_bounds__(kBlock, 2) dupire_europeans_multi_kernel(const
     for (int i = tid; i < nPay; i += kBlock) ks[i] = a.ksorted[i];
     for (int i = tid; i <= D; i += kBlock) isev[i] = a.is_event[i];
     for (int i = tid; i < kWarps * nPay; i += kBlock) payRows[i] = 0.0;
+    for (int i = tid; i < a.lut_n; i += kBlock) lutS[i] = a.lut[i];
     if (kSobol) sobol_load_low(dirlow, a.sobol_dir, a.dim);
     __syncthreads();
     double* myPay = payRows + size_t(warp) * nPay;
     double* fw = payRows + size_t(kWarps) * nPay + size_t(warp) * 32;
 
     Locator loc;
-    loc.x = xs; loc.lut = nullptr; loc.m = m; loc.lutN = 0; loc.x0 = 0.0; loc.scale = 0.0;
+    loc.x = xs; loc.lut = lutS; loc.m = m; loc.lutN = a.lut_n; loc.x0 = a.lut_x0; loc.scale = a.lut_scale;
     loc.p2 = 1;
     while (loc.p2 * 2 <= m) loc.p2 *= 2;
 

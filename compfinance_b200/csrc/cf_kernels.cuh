@@ -123,12 +123,22 @@ struct PayCtx {
     __device__ __forceinline__ void ladder(int k0, int n, const double* __restrict__ K, double F, double num)
     {
         warp_ladder_sums(fw, F, valid, K + k0, n, num, myPay + k0, lane);
-        if (w || perPath) {
+        if (perPath) {
             for (int k = k0; k < k0 + n; ++k) {
                 const double v = div_n(fmax(F - __ldg(K + k), 0.0), num);
                 if (w) agg += __ldg(w + k) * v;
-                if (perPath) perPath[k] = v;
+                perPath[k] = v;
             }
+        } else if (w) {
+            // this path's share of the aggregate: the weighted positive parts first, one division for the ladder
+            double a0 = 0.0, a1 = 0.0;
+            int k = k0;
+            for (; k + 1 < k0 + n; k += 2) {
+                a0 = fma(__ldg(w + k), pos_part(F - __ldg(K + k)), a0);
+                a1 = fma(__ldg(w + k + 1), pos_part(F - __ldg(K + k + 1)), a1);
+            }
+            if (k < k0 + n) a0 = fma(__ldg(w + k), pos_part(F - __ldg(K + k)), a0);
+            agg += div_n(a0 + a1, num);
         }
     }
 };
@@ -244,14 +254,17 @@ template <> struct Product<CF_PRODUCT_EUROPEANS> {
         SampleAdj r = {0.0, 0.0, 0.0, 0.0};
         const double F = s.fwd(), num = s.num();
         const int k1 = __ldg(off + e + 1);
+        // max(x, 0) has derivative 1 iff x > 0 (AADExpr.h:571-583): the weights of the strikes in the money and their
+        // moneyness, branch-free, then one division each for the ladder
+        double sw = 0.0, swx = 0.0;
         for (int k = __ldg(off + e); k < k1; ++k) {
             const double x = F - __ldg(K + k);
-            if (x > 0.0) {                               // max(x, 0): derivative 1 iff x > 0 (AADExpr.h:571-583)
-                const double wk = __ldg(w + k);
-                r.fwd += div_n(wk, num);
-                r.num -= div_n(wk * x, num * num);
-            }
+            const double wk = x > 0.0 ? __ldg(w + k) : 0.0;
+            sw += wk;
+            swx = fma(wk, x, swx);
         }
+        r.fwd = div_n(sw, num);
+        r.num = -div_n(swx, num * num);
         return r;
     }
 };

@@ -13,16 +13,9 @@
 #pragma once
 
 #include "cf_base.h"
+#include "cf_products.h"      // cfprd::fixed2
 
 namespace cfprd {
-
-// a number with two decimals, the way the reference's labels print dates and strikes
-inline std::string fixed2(const double x)
-{
-    std::ostringstream text;
-    text << std::fixed << std::setprecision(2) << x;
-    return text.str();
-}
 
 // whole percent / whole months of the Autocall label: int(100 x + EPS)
 inline std::string whole(const double x) { return std::to_string(int(x + EPS)); }

@@ -38,7 +38,7 @@ __host__ __device__ inline BsSmemR bs_smem_rev(int D, int E)
     BsSmemR s{};
     s.ds = align16(sizeof(double2) * size_t(D + 1));
     s.bits = align16(sizeof(uint32_t) * ((D + 31) / 32 + 1));
-    s.live = align16(sizeof(uint32_t) * (2 * kBsMaxWords + 1 + kBsRevWarps));
+    s.live = align16(sizeof(uint32_t) * (2 * kBsMaxWords + 4 + kBsRevWarps));      // masks, prefix (+ 1), warp totals on their own 16 bytes
     s.rows = align16(sizeof(double) * size_t(bs_adj_size(D, E))) * kBsRevWarps;
     s.red = align16(sizeof(double) * kBsRevWarps);
     s.total = s.ds + s.bits + s.live + s.rows + s.red;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kBsRevBlock, 1) bs_reverse_span_kernel(const D
     uint32_t* bitS = reinterpret_cast<uint32_t*>(p);     p += z.bits;
     uint32_t* maskS = reinterpret_cast<uint32_t*>(p);
     uint32_t* prefS = maskS + kBsMaxWords;
-    uint32_t* wtotS = prefS + kBsMaxWords + 1;         p += z.live;
+    uint32_t* wtotS = prefS + kBsMaxWords + 4;         p += z.live;      // 16-byte aligned: a widened load of the totals never touches the prefix array
     double* rowsS = reinterpret_cast<double*>(p);        p += z.rows;
     double* red = reinterpret_cast<double*>(p);
     const size_t rowStride = align16(sizeof(double) * size_t(nAdj)) / sizeof(double);

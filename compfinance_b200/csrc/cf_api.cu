@@ -157,9 +157,48 @@ std::unique_ptr<DeviceCtx> open_device(int id, int index, bool withWorker)
 
 void retire_plans();     // the plans of the context go with it (defined after cf_plan)
 
+// Pinned result blocks of host-buffer runs, kept across plans: cudaHostAlloc / cudaFreeHost cost about a millisecond
+// each, which a one-shot cf_run_* (a plan per call) paid on every call.
+struct PinnedCache {
+    std::mutex m;
+    std::vector<std::pair<double*, size_t>> blocks;
+    double* take(size_t n, size_t& cap)
+    {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            size_t best = blocks.size();
+            for (size_t i = 0; i < blocks.size(); ++i)
+                if (blocks[i].second >= n && (best == blocks.size() || blocks[i].second < blocks[best].second)) best = i;
+            if (best < blocks.size()) {
+                double* p = blocks[best].first; cap = blocks[best].second;
+                blocks.erase(blocks.begin() + long(best));
+                return p;
+            }
+        }
+        double* p = nullptr;
+        cap = std::max<size_t>(n, 2048);
+        CF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p), cap * sizeof(double), cudaHostAllocPortable));
+        return p;
+    }
+    void give(double* p, size_t cap)
+    {
+        if (!p) return;
+        std::lock_guard<std::mutex> lock(m);
+        if (blocks.size() < 8) blocks.emplace_back(p, cap); else cudaFreeHost(p);
+    }
+    void clear()
+    {
+        std::lock_guard<std::mutex> lock(m);
+        for (auto& b : blocks) cudaFreeHost(b.first);
+        blocks.clear();
+    }
+};
+PinnedCache g_pinned;
+
 void close_devices()
 {
     retire_plans();
+    g_pinned.clear();
     for (auto& d : g_devs) {
         if (d->worker) d->worker->stop();
         cudaSetDevice(d->id);
@@ -1510,17 +1549,16 @@ struct cf_plan {
     double* pinned(size_t n)
     {
         if (hostCap < n) {
-            if (hostOut) cudaFreeHost(hostOut);
+            g_pinned.give(hostOut, hostCap);
             hostOut = nullptr; hostCap = 0;
-            CF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&hostOut), n * sizeof(double), cudaHostAllocPortable));
-            hostCap = n;
+            hostOut = g_pinned.take(n, hostCap);
         }
         return hostOut;
     }
     ~cf_plan()
     {
         retire();
-        if (hostOut) cudaFreeHost(hostOut);
+        g_pinned.give(hostOut, hostCap);
         if (t_dev) cudaSetDevice(t_dev->id);
         auto& v = live_plans();
         v.erase(std::remove(v.begin(), v.end(), this), v.end());

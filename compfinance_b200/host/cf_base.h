@@ -272,6 +272,13 @@ inline bool cfDirectTargets(CfSession& s, const std::vector<Number*>& params)
 {
     if (s.directState == 0) {
         const auto& targets = s.setup.mdl.adjointTargets;
+        // the common case first: target q IS parameter q (Dupire with its time map lists spot and vols in parameter order)
+        if (targets.size() == params.size() && std::equal(targets.begin(), targets.end(), params.begin())) {
+            s.directParam.resize(targets.size());
+            std::iota(s.directParam.begin(), s.directParam.end(), 0);
+            s.directState = 1;
+            return true;
+        }
         std::unordered_map<const Number*, int> where;
         for (size_t j = 0; j < params.size(); ++j) where.emplace(params[j], int(j));
         s.directParam.assign(targets.size(), -1);
